@@ -1,0 +1,702 @@
+// Implicit-GEMM 3-D convolution on tcgen05 tensor cores (sm_100a): forward, data-gradient and
+// weight-gradient kernels plus the weight packer.
+//
+// Replaces nn.Conv3d + the statistics half of nn.BatchNorm3d of the reference
+// (backbone/s3dg.py:8-28 BasicConv3d, :30-65 STConv3d; model/pretrain.py:52,54) and the cuDNN
+// dgrad / wgrad that loss.backward() (main_nce.py:330) dispatches.
+//
+// Design:
+//  * activations are channels-last fp32 in HBM, *pre*-BatchNorm; the consumer applies
+//    relu(scale*x+shift) while it gathers its operand tile (BN-apply + ReLU never touch HBM);
+//  * producer warps gather 128 pixels x 64 K-elements, split every value into a 16-bit (hi, lo)
+//    pair and store both into 128B-swizzled shared-memory tiles; weights arrive pre-split and
+//    pre-swizzled through one bulk (TMA-engine) copy per stage;
+//  * one elected thread issues tcgen05.mma (M=128, N<=256, K=16) for the three products
+//    hi*lo, lo*hi, hi*hi into one fp32 TMEM accumulator (fp32-equivalent result), or hi*hi only
+//    in single-pass mode;
+//  * four epilogue warps drain a second TMEM accumulator of the previous tile concurrently,
+//    transpose through shared memory for coalesced stores and accumulate the per-channel
+//    sum / sum-of-squares that train-mode BatchNorm needs.
+#include "common.cuh"
+#include "coclr_b200.h"
+
+namespace coclr {
+
+static constexpr int kTileM = 128;      // pixels per tile (UMMA M)
+static constexpr int kChunkK = 64;      // K elements per pipeline stage (one 128B swizzle row)
+static constexpr int kProducerWarps = 8;
+static constexpr int kEpiWarps = 4;
+// warp roles: [0,4) epilogue, [4,12) producers, 12 MMA issuer, 13 weight loader + TMEM owner
+static constexpr int kThreads = (kEpiWarps + kProducerWarps + 2) * 32;
+static constexpr int kStagePitch = 33;  // floats per staged row (conflict-free transpose)
+
+struct RowSet8 {
+  int b[8], t[8], y[8], x[8];  // b < 0 : row outside the problem
+};
+
+// Decompose destination pixel m into the source-space base coordinates used by the gather.
+COCLR_DEVINL void row_coords(const coclr_geom_t& G, int Td, int Hd, int Wd, int M, int m, int& b, int& t, int& y,
+                             int& x) {
+  if (m >= M) {
+    b = -1;
+    t = y = x = 0;
+    return;
+  }
+  int xx = m % Wd;
+  int r = m / Wd;
+  int yy = r % Hd;
+  r /= Hd;
+  int tt = r % Td;
+  b = r / Td;
+  if (!G.transposed) {
+    t = tt * G.st - G.pt;
+    y = yy * G.sh - G.ph;
+    x = xx * G.sw - G.pw;
+  } else {
+    t = tt + G.pt;
+    y = yy + G.ph;
+    x = xx + G.pw;
+  }
+}
+
+// Gather NI*16 rows x 64 K-columns [kbase, kbase+64) of the implicit operand into one swizzled
+// [rows][128 B] block (hi) and its lo twin.  Thread (kg, r0) owns 4 consecutive K elements of rows
+// r0 + 16*i.  K index k = tap*C + channel; C % 4 == 0 so a float4 never straddles taps.
+template <bool kBf16, bool kLo, int NI>
+COCLR_DEVINL void gather_block(const coclr_src_t& S, const coclr_geom_t& G, int Kreal, int kbase, int kg, int r0,
+                               const int* rb, const int* rt, const int* ry, const int* rx, uint8_t* blk_hi,
+                               uint8_t* blk_lo) {
+  const int k0 = kbase + kg * 4;
+  const bool kvalid = k0 < Kreal;
+  int ta = 0, ya = 0, xa = 0, ci = 0;
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (kvalid) {
+    int tap = k0 / S.C;
+    ci = k0 - tap * S.C;
+    int khw = G.kh * G.kw;
+    ta = tap / khw;
+    int rem = tap - ta * khw;
+    ya = rem / G.kw;
+    xa = rem - ya * G.kw;
+    if (S.scale != nullptr) {
+      sc = __ldg(reinterpret_cast<const float4*>(S.scale + ci));
+      sh = __ldg(reinterpret_cast<const float4*>(S.shift + ci));
+    }
+  }
+  float4 v[NI];
+  bool ok[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    ok[i] = false;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kvalid && rb[i] >= 0) {
+      int ts, ys, xs;
+      bool in;
+      if (!G.transposed) {
+        ts = rt[i] + ta;
+        ys = ry[i] + ya;
+        xs = rx[i] + xa;
+        in = true;
+      } else {
+        ts = rt[i] - ta;
+        ys = ry[i] - ya;
+        xs = rx[i] - xa;
+        in = (ts >= 0) && (ys >= 0) && (xs >= 0);
+        if (G.st == 2) { in = in && !(ts & 1); ts >>= 1; }
+        if (G.sh == 2) { in = in && !(ys & 1); ys >>= 1; }
+        if (G.sw == 2) { in = in && !(xs & 1); xs >>= 1; }
+      }
+      in = in && ((unsigned)ts < (unsigned)S.T) && ((unsigned)ys < (unsigned)S.H) && ((unsigned)xs < (unsigned)S.W);
+      if (in) {
+        size_t off = ((((size_t)rb[i] * S.T + ts) * S.H + ys) * S.W + xs) * (size_t)S.ld + S.coff + ci;
+        v[i] = ldg_nc_f4(S.ptr + off);
+        ok[i] = true;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    float4 a = v[i];
+    if (ok[i]) {
+      a.x = fmaf(a.x, sc.x, sh.x);
+      a.y = fmaf(a.y, sc.y, sh.y);
+      a.z = fmaf(a.z, sc.z, sh.z);
+      a.w = fmaf(a.w, sc.w, sh.w);
+      if (S.relu) {
+        a.x = fmaxf(a.x, 0.f);
+        a.y = fmaxf(a.y, 0.f);
+        a.z = fmaxf(a.z, 0.f);
+        a.w = fmaxf(a.w, 0.f);
+      }
+    }
+    uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+    split2<kBf16>(a.x, h0, l0);
+    split2<kBf16>(a.y, h1, l1);
+    split2<kBf16>(a.z, h2, l2);
+    split2<kBf16>(a.w, h3, l3);
+    const uint32_t off = swz128_offset((uint32_t)(r0 + 16 * i), (uint32_t)(kg >> 1)) + (uint32_t)(kg & 1) * 8u;
+    *reinterpret_cast<uint2*>(blk_hi + off) =
+        make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+    if constexpr (kLo) {
+      *reinterpret_cast<uint2*>(blk_lo + off) =
+          make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward / dgrad kernel
+// ------------------------------------------------------------------------------------------------
+struct ConvSmemLayout {
+  uint32_t a_bytes;      // per copy (hi or lo)
+  uint32_t b_bytes;      // per copy
+  uint32_t stage_bytes;  // all copies of A and B of one stage
+  uint32_t stages;
+  uint32_t off_stage;    // transpose staging for the epilogue
+  uint32_t off_stats;    // double [2][n_tiles*BN]
+  uint32_t off_bars;
+  uint32_t total;
+};
+
+__host__ __device__ inline ConvSmemLayout conv_smem_layout(int BN, int n_tiles, int npass, int want_stats) {
+  ConvSmemLayout L;
+  const uint32_t copies = npass > 1 ? 2u : 1u;
+  L.a_bytes = kTileM * 128u;
+  L.b_bytes = (uint32_t)BN * 128u;
+  L.stage_bytes = copies * (L.a_bytes + L.b_bytes);
+  const uint32_t fixed = kEpiWarps * 32u * kStagePitch * 4u + (want_stats ? 2u * n_tiles * BN * 8u : 0u) + 256u;
+  const uint32_t budget = 227u * 1024u - 1024u /*alignment slack*/ - fixed;
+  uint32_t st = budget / L.stage_bytes;
+  if (st > 6) st = 6;
+  L.stages = st;
+  L.off_stage = L.stages * L.stage_bytes;
+  L.off_stats = L.off_stage + kEpiWarps * 32u * kStagePitch * 4u;
+  L.off_bars = L.off_stats + (want_stats ? 2u * n_tiles * BN * 8u : 0u);
+  L.total = L.off_bars + 256u + 1024u;
+  return L;
+}
+
+template <bool kBf16, int kNPass>
+__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_conv_t P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr bool kLo = kNPass > 1;
+  const int M = P.B * P.Td * P.Hd * P.Wd;
+  const int nkc = (P.Kreal + kChunkK - 1) / kChunkK;
+  const int m_tiles = (M + kTileM - 1) / kTileM;
+  const int total_tiles = m_tiles * P.n_tiles;
+  const ConvSmemLayout L = conv_smem_layout(P.BN, P.n_tiles, kNPass, P.stats != nullptr);
+  const uint32_t nstages = L.stages;
+
+  float* stage_buf = reinterpret_cast<float*>(smem + L.off_stage);
+  double* sstats = reinterpret_cast<double*>(smem + L.off_stats);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.off_bars);  // [6]
+  uint64_t* empty_bar = full_bar + 6;                                    // [6]
+  uint64_t* tfull_bar = empty_bar + 6;                                   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                                  // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < 6; ++s) {
+      mbar_init(&full_bar[s], kProducerWarps + 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (P.stats != nullptr) {
+    for (int i = threadIdx.x; i < 2 * P.n_tiles * P.BN; i += kThreads) sstats[i] = 0.0;
+  }
+  if (warp == 13) {
+    tmem_alloc<512>(tmem_holder);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp >= kEpiWarps && warp < kEpiWarps + kProducerWarps) {
+    // ===================== A-operand producers =====================
+    const int pt = threadIdx.x - kEpiWarps * 32;  // 0..255
+    const int kg = pt & 15;
+    const int r0 = pt >> 4;
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / P.n_tiles;
+      int rb[8], rt[8], ry[8], rx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        row_coords(P.g, P.Td, P.Hd, P.Wd, M, m_tile * kTileM + r0 + 16 * i, rb[i], rt[i], ry[i], rx[i]);
+      for (int kc = 0; kc < nkc; ++kc) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = smem + stage * L.stage_bytes;
+        gather_block<kBf16, kLo, 8>(P.src, P.g, P.Kreal, kc * kChunkK, kg, r0, rb, rt, ry, rx, sa, sa + L.a_bytes);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[stage]);
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 13) {
+    // ===================== weight loader (bulk copies) =====================
+    if (lane == 0) {
+      const uint32_t copies = kLo ? 2u : 1u;
+      const uint32_t bytes = copies * L.b_bytes;
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % P.n_tiles;
+        for (int kc = 0; kc < nkc; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sb = smem + stage * L.stage_bytes + (kLo ? 2u : 1u) * L.a_bytes;
+          const uint8_t* src =
+              reinterpret_cast<const uint8_t*>(P.wpk) + ((size_t)n_tile * nkc + kc) * (size_t)(2u * L.b_bytes);
+          mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          bulk_g2s(sb, src, bytes, &full_bar[stage]);
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 12) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(kBf16 ? 1u : 0u, 0u, 0u, kTileM, (uint32_t)P.BN);
+    uint32_t stage = 0, phase = 0;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * 256u;
+      for (int kc = 0; kc < nkc; ++kc) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * L.stage_bytes);
+          const uint32_t sb = sa + (kLo ? 2u : 1u) * L.a_bytes;
+          const uint64_t a_hi = make_smem_desc(sa, 16, 1024);
+          const uint64_t b_hi = make_smem_desc(sb, 16, 1024);
+          if constexpr (kLo) {
+            const uint64_t a_lo = make_smem_desc(sa + L.a_bytes, 16, 1024);
+            const uint64_t b_lo = make_smem_desc(sb + L.b_bytes, 16, 1024);
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, (kc | k) != 0);
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+          } else {
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (kc | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kc == nkc - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp < kEpiWarps) {
+    // ===================== epilogue =====================
+    float* my_stage = stage_buf + warp * 32 * kStagePitch;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m_tile = tile / P.n_tiles;
+      const int n_tile = tile % P.n_tiles;
+      const uint32_t acc = it & 1u;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row_base = m_tile * kTileM + warp * 32;
+      for (int c0 = 0; c0 < P.BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 256u + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) my_stage[lane * kStagePitch + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int col = n_tile * P.BN + c0 + lane;  // global output channel handled by this lane
+        const bool col_ok = col < P.N && (c0 + lane) < P.BN;
+        const float us = (P.wunscale != nullptr && col_ok) ? __ldg(P.wunscale + n_tile * P.BN + c0 + lane) : 1.f;
+        float s1 = 0.f, s2 = 0.f;
+        if (col_ok) {
+          float* dcol = P.dst + P.dst_coff + col;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const int m = row_base + r;
+            if (m < M) {
+              float val = my_stage[r * kStagePitch + lane] * us;
+              float* d = dcol + (size_t)m * P.dst_ld;
+              if (P.accumulate) val += *d;
+              *d = val;
+              s1 += val;
+              s2 += val * val;
+            }
+          }
+          if (P.stats != nullptr) {
+            atomicAdd(&sstats[col], (double)s1);
+            atomicAdd(&sstats[P.n_tiles * P.BN + col], (double)s2);
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+    if (P.stats != nullptr) {
+      named_bar_sync(1, kEpiWarps * 32);
+      for (int c = threadIdx.x; c < P.N; c += kEpiWarps * 32) {
+        atomicAdd(&P.stats[c], sstats[c]);
+        atomicAdd(&P.stats[P.N + c], sstats[P.n_tiles * P.BN + c]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight-gradient kernel: D[cout (128 lanes), kcol (<=256)] = sum over pixels dY[px, cout] * A[px, kcol]
+// both operands are MN-major (the 64-element swizzle rows run along cout / kcol, pixels are K).
+// ------------------------------------------------------------------------------------------------
+static constexpr int kWgPx = 64;  // pixels per pipeline stage
+
+struct WgradSmemLayout {
+  uint32_t dy_bytes;   // per copy: 2 blocks of [64 px][128 B]
+  uint32_t a_bytes;    // per copy: nblk blocks
+  uint32_t stage_bytes;
+  uint32_t stages;
+  uint32_t off_bars;
+  uint32_t total;
+};
+__host__ __device__ inline WgradSmemLayout wgrad_smem_layout(int BNk, int npass) {
+  WgradSmemLayout L;
+  const uint32_t copies = npass > 1 ? 2u : 1u;
+  L.dy_bytes = 2u * kWgPx * 128u;
+  L.a_bytes = (uint32_t)(BNk / 64) * kWgPx * 128u;
+  L.stage_bytes = copies * (L.dy_bytes + L.a_bytes);
+  uint32_t st = (227u * 1024u - 2048u) / L.stage_bytes;
+  if (st > 6) st = 6;
+  L.stages = st;
+  L.off_bars = L.stages * L.stage_bytes;
+  L.total = L.off_bars + 256u + 1024u;
+  return L;
+}
+
+__host__ __device__ inline int wgrad_bnk(int Kreal) {
+  // width of one K-column tile: multiple of 64, at most 256, balanced over the tiles
+  int kt = (Kreal + 255) / 256;
+  int w = (Kreal + kt - 1) / kt;
+  return ((w + 63) / 64) * 64;
+}
+
+template <bool kBf16, int kNPass>
+__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgrad_t P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr bool kLo = kNPass > 1;
+  const int M = P.B * P.Td * P.Hd * P.Wd;
+  const int taps = P.g.kt * P.g.kh * P.g.kw;
+  const int Kreal = taps * P.src.C;
+  const int BNk = wgrad_bnk(Kreal);
+  const int k_tiles = (Kreal + BNk - 1) / BNk;
+  const int c_tiles = (P.Cout + 127) / 128;
+  const WgradSmemLayout L = wgrad_smem_layout(BNk, kNPass);
+  const uint32_t nstages = L.stages;
+
+  // work item: (split, c_tile, k_tile)
+  int w = blockIdx.x;
+  const int k_tile = w % k_tiles;
+  w /= k_tiles;
+  const int c_tile = w % c_tiles;
+  const int split = w / c_tiles;
+  const int chunks_total = (M + kWgPx - 1) / kWgPx;
+  const int chunks_per = (chunks_total + P.splits - 1) / P.splits;
+  const int ch_begin = split * chunks_per;
+  const int ch_end = min(chunks_total, ch_begin + chunks_per);
+  const int nch = max(0, ch_end - ch_begin);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.off_bars);  // [6]
+  uint64_t* empty_bar = full_bar + 6;
+  uint64_t* tfull_bar = empty_bar + 6;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tfull_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < 6; ++s) {
+      mbar_init(&full_bar[s], kProducerWarps);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tfull_bar[0], 1);
+    mbar_fence_init();
+  }
+  if (warp == 13) tmem_alloc<256>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp >= kEpiWarps && warp < kEpiWarps + kProducerWarps) {
+    const int pt = threadIdx.x - kEpiWarps * 32;
+    const int kg = pt & 15;
+    const int r0 = pt >> 4;  // rows r0 + 16*i, i < 4
+    uint32_t stage = 0, phase = 0;
+    coclr_geom_t ident;
+    ident.kt = ident.kh = ident.kw = 1;
+    ident.st = ident.sh = ident.sw = 1;
+    ident.pt = ident.ph = ident.pw = 0;
+    ident.transposed = 0;
+    for (int ch = ch_begin; ch < ch_begin + nch; ++ch) {
+      int rb[4], rt[4], ry[4], rx[4];    // source-space bases for the activation gather
+      int qb[4], qt[4], qy[4], qx[4];    // plain destination coordinates for dY
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = ch * kWgPx + r0 + 16 * i;
+        row_coords(P.g, P.Td, P.Hd, P.Wd, M, m, rb[i], rt[i], ry[i], rx[i]);
+        row_coords(ident, P.Td, P.Hd, P.Wd, M, m, qb[i], qt[i], qy[i], qx[i]);
+      }
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      uint8_t* s_dy = smem + stage * L.stage_bytes;
+      uint8_t* s_a = s_dy + (kLo ? 2u : 1u) * L.dy_bytes;
+      // dY: 2 blocks of 64 output channels
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        gather_block<kBf16, kLo, 4>(P.dy, ident, P.dy.C, c_tile * 128 + blk * 64, kg, r0, qb, qt, qy, qx,
+                                    s_dy + blk * (kWgPx * 128), s_dy + L.dy_bytes + blk * (kWgPx * 128));
+      }
+      for (int blk = 0; blk < BNk / 64; ++blk) {
+        gather_block<kBf16, kLo, 4>(P.src, P.g, Kreal, k_tile * BNk + blk * 64, kg, r0, rb, rt, ry, rx,
+                                    s_a + blk * (kWgPx * 128), s_a + L.a_bytes + blk * (kWgPx * 128));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+      if (++stage == nstages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 12) {
+    const uint32_t idesc = make_idesc(kBf16 ? 1u : 0u, 1u, 1u, 128u, (uint32_t)BNk);
+    uint32_t stage = 0, phase = 0;
+    for (int ch = 0; ch < nch; ++ch) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t s_dy = smem_u32(smem + stage * L.stage_bytes);
+        const uint32_t s_a = s_dy + (kLo ? 2u : 1u) * L.dy_bytes;
+        // MN-major: LBO = stride between 64-element MN blocks (64 px * 128 B), SBO = 8-pixel group stride
+        const uint64_t a_hi = make_smem_desc(s_dy, kWgPx * 128, 1024);
+        const uint64_t b_hi = make_smem_desc(s_a, kWgPx * 128, 1024);
+        // one K=16 step = 16 pixels = 2 swizzle atoms = 2048 B -> +128 in descriptor units
+        if constexpr (kLo) {
+          const uint64_t a_lo = make_smem_desc(s_dy + L.dy_bytes, kWgPx * 128, 1024);
+          const uint64_t b_lo = make_smem_desc(s_a + L.a_bytes, kWgPx * 128, 1024);
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_base, a_hi + 128 * k, b_lo + 128 * k, idesc, (ch | k) != 0);
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_base, a_lo + 128 * k, b_hi + 128 * k, idesc, 1u);
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_base, a_hi + 128 * k, b_hi + 128 * k, idesc, 1u);
+        } else {
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_base, a_hi + 128 * k, b_hi + 128 * k, idesc, (ch | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (ch == nch - 1) umma_commit(&tfull_bar[0]);
+      }
+      __syncwarp();
+      if (++stage == nstages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp < kEpiWarps) {
+    if (nch > 0) {
+      mbar_wait(&tfull_bar[0], 0);
+      tc_fence_after();
+      const int n = c_tile * 128 + warp * 32 + lane;  // output channel of this thread
+      for (int c0 = 0; c0 < BNk; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (n < P.Cout) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int k = k_tile * BNk + c0 + j;
+            if (k < Kreal) {
+              const int tap = k / P.src.C;
+              const int ci = k - tap * P.src.C;
+              if (ci < P.Cin_real)
+                atomicAdd(P.dw + ((size_t)n * P.Cin_real + ci) * taps + tap, __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packer: one CTA per packed row
+// ------------------------------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void pack_weights_kernel(const coclr_pack_t P, int N, int BN, int n_tiles, int Kreal, int nkc) {
+  const int row = blockIdx.x;  // 0 .. n_tiles*BN
+  const int n_tile = row / BN;
+  const int rin = row - n_tile * BN;
+  const int n = n_tile * BN + rin;  // tiles are contiguous in n
+  __shared__ float red[32];
+  const int Kpad = nkc * kChunkK;
+  auto wval = [&](int k) -> float {
+    if (n >= N || k >= Kreal) return 0.f;
+    const int tap = k / P.Cpad;
+    const int c = k - tap * P.Cpad;
+    if (P.mode == 0) {
+      if (c >= P.Cin) return 0.f;
+      return P.w[((size_t)n * P.Cin + c) * P.taps + tap];
+    } else {
+      if (c >= P.Cout) return 0.f;
+      return P.w[((size_t)c * P.Cin + n) * P.taps + tap];
+    }
+  };
+  float mx = 0.f;
+  for (int k = threadIdx.x; k < Kreal; k += blockDim.x) mx = fmaxf(mx, fabsf(wval(k)));
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float m2 = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    if (threadIdx.x == 0) red[0] = m2;
+  }
+  __syncthreads();
+  mx = red[0];
+  float scale = 1.f, unscale = 1.f;
+  if (mx > 0.f && isfinite(mx)) {
+    int e;
+    frexpf(mx, &e);  // mx = f * 2^e, f in [0.5, 1)
+    e = max(-100, min(100, e));
+    scale = ldexpf(1.f, -e);
+    unscale = ldexpf(1.f, e);
+  }
+  if (threadIdx.x == 0) P.unscale[row] = unscale;
+  uint8_t* base = reinterpret_cast<uint8_t*>(P.wpk);
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    const float v = wval(k) * scale;
+    uint16_t hi, lo;
+    split2<kBf16>(v, hi, lo);
+    const int kc = k / kChunkK;
+    const int kk = k - kc * kChunkK;
+    const size_t img = ((size_t)n_tile * nkc + kc) * 2;
+    const uint32_t off = swz128_offset((uint32_t)rin, (uint32_t)(kk >> 3)) + (uint32_t)(kk & 7) * 2u;
+    *reinterpret_cast<uint16_t*>(base + (img + 0) * (size_t)BN * 128 + off) = hi;
+    *reinterpret_cast<uint16_t*>(base + (img + 1) * (size_t)BN * 128 + off) = lo;
+  }
+}
+
+static inline void tile_plan(int N, int* BN, int* n_tiles) {
+  int nt = (N + 255) / 256;
+  int w = (N + nt - 1) / nt;
+  *BN = ((w + 31) / 32) * 32;
+  *n_tiles = nt;
+}
+
+}  // namespace coclr
+
+using namespace coclr;
+
+extern "C" size_t coclr_conv_packed_bytes(int N, int Kreal, int* BN_out, int* n_tiles_out) {
+  int BN, nt;
+  tile_plan(N, &BN, &nt);
+  if (BN_out) *BN_out = BN;
+  if (n_tiles_out) *n_tiles_out = nt;
+  const int nkc = (Kreal + kChunkK - 1) / kChunkK;
+  return (size_t)nt * nkc * 2 * BN * 128;
+}
+
+extern "C" int coclr_pack_weights(const coclr_pack_t* p, coclr_stream_t stream) {
+  if (!p || !p->w || !p->wpk || !p->unscale) return COCLR_E_ARG;
+  const int N = p->mode == 0 ? p->Cout : p->Cin;
+  const int Kreal = p->taps * p->Cpad;
+  int BN, nt;
+  tile_plan(N, &BN, &nt);
+  const int nkc = (Kreal + kChunkK - 1) / kChunkK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p->bf16)
+    pack_weights_kernel<true><<<nt * BN, 128, 0, s>>>(*p, N, BN, nt, Kreal, nkc);
+  else
+    pack_weights_kernel<false><<<nt * BN, 128, 0, s>>>(*p, N, BN, nt, Kreal, nkc);
+  return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
+}
+
+template <bool B, int NP>
+static int launch_conv(const coclr_conv_t& P, int num_sms, cudaStream_t s) {
+  const int M = P.B * P.Td * P.Hd * P.Wd;
+  const int m_tiles = (M + kTileM - 1) / kTileM;
+  const int total = m_tiles * P.n_tiles;
+  const ConvSmemLayout L = conv_smem_layout(P.BN, P.n_tiles, NP, P.stats != nullptr);
+  if (L.stages < 2) return COCLR_E_ARG;
+  cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<B, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+  if (e != cudaSuccess) return COCLR_E_LAUNCH;
+  const int grid = total < num_sms ? total : num_sms;
+  conv_igemm_kernel<B, NP><<<grid, kThreads, L.total, s>>>(P);
+  return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
+}
+
+extern "C" int coclr_conv_igemm(const coclr_conv_t* p, int num_sms, coclr_stream_t stream) {
+  if (!p || !p->src.ptr || !p->wpk || !p->dst) return COCLR_E_ARG;
+  if (p->src.C % 4 != 0 || p->src.ld % 4 != 0 || p->src.coff % 4 != 0) return COCLR_E_ARG;
+  if (p->BN % 32 != 0 || p->BN > 256 || p->BN < 32 || p->n_tiles < 1) return COCLR_E_ARG;
+  if (p->Kreal != p->g.kt * p->g.kh * p->g.kw * p->src.C) return COCLR_E_ARG;
+  if ((p->g.st != 1 && p->g.st != 2) || (p->g.sh != 1 && p->g.sh != 2) || (p->g.sw != 1 && p->g.sw != 2))
+    return COCLR_E_ARG;
+  if (num_sms <= 0) return COCLR_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p->bf16) {
+    return p->npass > 1 ? launch_conv<true, 3>(*p, num_sms, s) : launch_conv<true, 1>(*p, num_sms, s);
+  } else {
+    return p->npass > 1 ? launch_conv<false, 3>(*p, num_sms, s) : launch_conv<false, 1>(*p, num_sms, s);
+  }
+}
+
+template <bool B, int NP>
+static int launch_wgrad(const coclr_wgrad_t& P, cudaStream_t s) {
+  const int taps = P.g.kt * P.g.kh * P.g.kw;
+  const int Kreal = taps * P.src.C;
+  const int BNk = wgrad_bnk(Kreal);
+  const int k_tiles = (Kreal + BNk - 1) / BNk;
+  const int c_tiles = (P.Cout + 127) / 128;
+  const WgradSmemLayout L = wgrad_smem_layout(BNk, NP);
+  if (L.stages < 2) return COCLR_E_ARG;
+  cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<B, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+  if (e != cudaSuccess) return COCLR_E_LAUNCH;
+  const int grid = k_tiles * c_tiles * P.splits;
+  conv_wgrad_kernel<B, NP><<<grid, kThreads, L.total, s>>>(P);
+  return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
+}
+
+extern "C" int coclr_conv_wgrad(const coclr_wgrad_t* p, coclr_stream_t stream) {
+  if (!p || !p->src.ptr || !p->dy.ptr || !p->dw) return COCLR_E_ARG;
+  if (p->src.C % 4 != 0 || p->src.ld % 4 != 0 || p->src.coff % 4 != 0) return COCLR_E_ARG;
+  if (p->dy.C % 4 != 0 || p->dy.ld % 4 != 0 || p->dy.coff % 4 != 0) return COCLR_E_ARG;
+  if (p->splits < 1 || p->g.transposed) return COCLR_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p->bf16) {
+    return p->npass > 1 ? launch_wgrad<true, 3>(*p, s) : launch_wgrad<true, 1>(*p, s);
+  } else {
+    return p->npass > 1 ? launch_wgrad<false, 3>(*p, s) : launch_wgrad<false, 1>(*p, s);
+  }
+}

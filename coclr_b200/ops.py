@@ -1,0 +1,73 @@
+"""Thin Python wrappers (torch tensors -> raw pointers) over the C ABI. No autograd here; the
+encoder-level autograd.Function lives in engine.py."""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+
+class Geometry:
+    """Conv geometry (kernel, stride, padding) per (t, h, w)."""
+
+    def __init__(self, k, s=(1, 1, 1), p=(0, 0, 0)):
+        self.k, self.s, self.p = tuple(k), tuple(s), tuple(p)
+
+    @property
+    def taps(self):
+        return self.k[0] * self.k[1] * self.k[2]
+
+    def out_dims(self, T, H, W):
+        return tuple((d + 2 * p - k) // s + 1 for d, k, s, p in zip((T, H, W), self.k, self.s, self.p))
+
+    def c(self, transposed=0):
+        return L.Geom(self.k[0], self.k[1], self.k[2], self.s[0], self.s[1], self.s[2],
+                      self.p[0], self.p[1], self.p[2], int(transposed))
+
+
+def make_src(x, coff, Cc, T, H, W, scale=None, shift=None, relu=False):
+    """x: fp32 CUDA tensor whose last dim is the per-pixel channel stride (channels-last rows)."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    return L.Src(L.dptr(x), x.shape[-1], coff, Cc, T, H, W, L.dptr(scale), L.dptr(shift), int(bool(relu)))
+
+
+def packed_layout(N, Kreal):
+    lib = L.load()
+    bn, nt = C.c_int(0), C.c_int(0)
+    nbytes = lib.coclr_conv_packed_bytes(N, Kreal, C.byref(bn), C.byref(nt))
+    return int(nbytes), bn.value, nt.value
+
+
+class PackedWeights:
+    """fp16/bf16 hi/lo swizzled tile images of one conv weight for one GEMM orientation."""
+
+    def __init__(self, Cout, Cin, taps, cpad, mode, bf16, device):
+        self.Cout, self.Cin, self.taps, self.cpad, self.mode, self.bf16 = Cout, Cin, taps, cpad, mode, int(bf16)
+        self.N = Cout if mode == 0 else Cin
+        self.Kreal = taps * cpad
+        nbytes, self.BN, self.n_tiles = packed_layout(self.N, self.Kreal)
+        self.wpk = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.unscale = torch.empty(self.BN * self.n_tiles, dtype=torch.float32, device=device)
+
+    def pack(self, w):
+        """w: PyTorch conv weight [Cout, Cin, kt, kh, kw] fp32 (contiguous, CUDA)."""
+        assert w.is_contiguous() and w.dtype == torch.float32
+        p = L.Pack(L.dptr(w), self.Cout, self.Cin, self.taps, self.cpad, self.mode, self.bf16,
+                   L.dptr(self.wpk), L.dptr(self.unscale))
+        L.check(L.load().coclr_pack_weights(C.byref(p), L.stream_ptr()), "coclr_pack_weights")
+        return self
+
+
+def conv_igemm(src, geom_c, B, dst_dims, pw, dst, dst_coff=0, accumulate=False, stats=None, npass=3):
+    """Run the implicit-GEMM conv. src: L.Src; geom_c: L.Geom; dst: [B,Td,Hd,Wd,ld] fp32."""
+    Td, Hd, Wd = dst_dims
+    p = L.Conv(src, geom_c, B, Td, Hd, Wd, pw.Kreal, L.dptr(pw.wpk), L.dptr(pw.unscale),
+               pw.N, pw.BN, pw.n_tiles, L.dptr(dst), dst.shape[-1], dst_coff, int(bool(accumulate)),
+               L.dptr(stats), npass, pw.bf16)
+    L.check(L.load().coclr_conv_igemm(C.byref(p), L.num_sms(), L.stream_ptr()), "coclr_conv_igemm")
+
+
+def conv_wgrad(src, geom_c, dy_src, B, dst_dims, Cout, Cin_real, dw, npass=3, bf16=True, splits=1):
+    Td, Hd, Wd = dst_dims
+    p = L.Wgrad(src, geom_c, dy_src, B, Td, Hd, Wd, Cout, Cin_real, L.dptr(dw), npass, int(bool(bf16)), splits)
+    L.check(L.load().coclr_conv_wgrad(C.byref(p), L.stream_ptr()), "coclr_conv_wgrad")
