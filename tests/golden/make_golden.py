@@ -1,0 +1,67 @@
+"""Generates tests/golden/infonce_cfg1.npz by running the UNMODIFIED reference (TengdaHan/CoCLR at
+/root/reference, model/pretrain.py InfoNCE) on BASELINE.json config 1 (S3D, moco-k=128, bs=4,
+seq_len=8, 128x128, CPU) from the deterministic synthetic state of oracle.coclr_oracle.synth_state.
+
+Run in the build container only:  python tests/golden/make_golden.py
+The .npz stores reference outputs (logits, loss, updated queue/ptr, selected gradients and
+post-EMA key weights); inputs are regenerated from seeds by the tests.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+
+def make_inputs(B=4, T=8, HW=128, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, 2, 3, T, HW, HW, generator=g)
+
+
+GRAD_KEYS = ["encoder_q.0.Conv_1a.conv1.weight", "encoder_q.0.Conv_1a.bn2.weight", "encoder_q.0.Conv_2c.conv2.weight",
+             "encoder_q.0.Mixed_3b.branch2.1.conv1.weight", "encoder_q.0.Mixed_4c.branch2.0.conv.weight",
+             "encoder_q.0.Mixed_4f.branch3.1.bn.bias", "encoder_q.0.Mixed_5c.branch1.1.conv2.weight",
+             "encoder_q.2.weight", "encoder_q.4.bias"]
+
+
+def run_reference(K=128, B=4, T=8, ptr=16, threads=8):
+    import torch.distributed as dist
+    sys.path.insert(0, REF)
+    from model.pretrain import InfoNCE  # the unmodified reference
+    from oracle import coclr_oracle as O
+    torch.set_num_threads(threads)
+    torch.Tensor.cuda = lambda self, *a, **k: self  # pretrain.py:112,185 hard-code .cuda(); CPU shim
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29581")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    torch.manual_seed(0)
+    model = InfoNCE("s3d", 128, K, 0.999, 0.07)
+    sd = O.synth_state(O.infonce_shapes(128, K), seed=0, ptr=ptr)
+    model.load_state_dict(O.with_aliases(sd), strict=True)
+    model.train()
+    block = make_inputs(B, T)
+    torch.manual_seed(77)  # fixes the torch.randperm draw of _batch_shuffle_ddp (pretrain.py:112)
+    logits, labels = model(block)
+    loss = torch.nn.CrossEntropyLoss()(logits, labels)
+    loss.backward()
+    out = {"logits": logits.detach().numpy(), "loss": np.float64(loss.item()),
+           "queue": model.queue.numpy().copy(), "queue_ptr": model.queue_ptr.numpy().copy()}
+    named = dict(model.named_parameters())
+    for k in GRAD_KEYS:
+        out["grad/" + k] = named[k].grad.numpy().copy()
+    out["ema/encoder_k.0.Conv_2c.conv1.weight"] = named["encoder_k.0.Conv_2c.conv1.weight"].detach().numpy().copy()
+    out["bn/encoder_q.0.Conv_1a.bn1.running_mean"] = model.state_dict()["encoder_q.0.Conv_1a.bn1.running_mean"].numpy().copy()
+    out["bn/encoder_k.0.Mixed_5c.branch0.0.bn.running_var"] = model.state_dict()["encoder_k.0.Mixed_5c.branch0.0.bn.running_var"].numpy().copy()
+    return out, model
+
+
+if __name__ == "__main__":
+    out, _ = run_reference()
+    np.savez_compressed(os.path.join(HERE, "infonce_cfg1.npz"), **out)
+    print("loss", out["loss"], "logits[0,:4]", out["logits"][0, :4])
