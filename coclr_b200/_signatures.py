@@ -4,6 +4,8 @@ import ctypes as C
 
 P = C.c_void_p
 I = C.c_int
+F = C.c_float
+LG = C.c_long
 
 # name -> (restype, argtypes)
 EXPORTS = {
@@ -11,6 +13,21 @@ EXPORTS = {
     "coclr_conv_packed_bytes": (C.c_size_t, [I, I, C.POINTER(I), C.POINTER(I)]),
     "coclr_conv_wgrad": (I, [P, P]),
     "coclr_pack_weights": (I, [P, P]),
+    "coclr_bn_finalize": (I, [P, P]),
+    "coclr_bn_bwd": (I, [P, I, P]),
+    "coclr_bias_relu_bwd": (I, [P, P, P, P, I, I, P]),
+    "coclr_maxpool_fwd": (I, [P, P]),
+    "coclr_maxpool_bwd": (I, [P, P]),
+    "coclr_avgpool_fwd": (I, [P, I, I, P, P, I, P, I, I, I, P]),
+    "coclr_avgpool_bwd": (I, [P, P, I, I, I, I, I, P]),
+    "coclr_pack_input": (I, [P, LG, LG, I, P, I, LG, P, P]),
+    "coclr_l2norm_fwd": (I, [P, P, P, P, I, I, P]),
+    "coclr_l2norm_bwd": (I, [P, P, P, P, P, I, I, P]),
+    "coclr_ema_update": (I, [P, P, F, F, LG, I, P]),
+    "coclr_queue_enqueue": (I, [P, P, I, I, I, I, P]),
+    "coclr_adam_step": (I, [P, I, P]),
+    "coclr_nce_logits_ce": (I, [P, P, P, F, I, I, I, P, P, P, P]),
+    "coclr_nce_logits_bwd": (I, [P, P, P, F, I, I, I, P, P]),
 }
 
 

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
   const int nkc = (P.Kreal + kChunkK - 1) / kChunkK;
   const int m_tiles = (M + kTileM - 1) / kTileM;
   const int total_tiles = m_tiles * P.n_tiles;
-  const ConvSmemLayout L = conv_smem_layout(P.BN, P.n_tiles, kNPass, P.stats != nullptr);
+  const ConvSmemLayout L = conv_smem_layout(P.BN, P.n_tiles, kNPass, P.stats_sum != nullptr);
   const uint32_t nstages = L.stages;
 
   float* stage_buf = reinterpret_cast<float*>(smem + L.off_stage);
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
     }
     mbar_fence_init();
   }
-  if (P.stats != nullptr) {
+  if (P.stats_sum != nullptr) {
     for (int i = threadIdx.x; i < 2 * P.n_tiles * P.BN; i += kThreads) sstats[i] = 0.0;
   }
   if (warp == 13) {
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
               s2 += val * val;
             }
           }
-          if (P.stats != nullptr) {
+          if (P.stats_sum != nullptr) {
             atomicAdd(&sstats[col], (double)s1);
             atomicAdd(&sstats[P.n_tiles * P.BN + col], (double)s2);
           }
@@ -349,11 +349,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
-    if (P.stats != nullptr) {
+    if (P.stats_sum != nullptr) {
       named_bar_sync(1, kEpiWarps * 32);
       for (int c = threadIdx.x; c < P.N; c += kEpiWarps * 32) {
-        atomicAdd(&P.stats[c], sstats[c]);
-        atomicAdd(&P.stats[P.N + c], sstats[P.n_tiles * P.BN + c]);
+        atomicAdd(&P.stats_sum[c], sstats[c]);
+        atomicAdd(&P.stats_sq[c], sstats[P.n_tiles * P.BN + c]);
       }
     }
   }
@@ -647,7 +647,7 @@ static int launch_conv(const coclr_conv_t& P, int num_sms, cudaStream_t s) {
   const int M = P.B * P.Td * P.Hd * P.Wd;
   const int m_tiles = (M + kTileM - 1) / kTileM;
   const int total = m_tiles * P.n_tiles;
-  const ConvSmemLayout L = conv_smem_layout(P.BN, P.n_tiles, NP, P.stats != nullptr);
+  const ConvSmemLayout L = conv_smem_layout(P.BN, P.n_tiles, NP, P.stats_sum != nullptr);
   if (L.stages < 2) return COCLR_E_ARG;
   cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<B, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return COCLR_E_LAUNCH;

@@ -1,0 +1,118 @@
+// MoCo / InfoNCE logits fused with temperature and cross-entropy (model/pretrain.py:175-182 +
+// nn.CrossEntropyLoss of main_nce.py:201,314): one launch produces logits = [q.k, q.queue]/T,
+// the per-row loss (label 0) and d(mean loss)/d(logits); a second small kernel turns any
+// d(logits) into d(q).  Latency-bound (B rows x (1+K) columns x 128), so plain FFMA with
+// coalesced reads of the [dim, K] queue (keys are columns, consecutive keys are contiguous).
+#include "common.cuh"
+#include "coclr_b200.h"
+
+namespace coclr {
+
+static constexpr int kNceThreads = 512;
+
+COCLR_DEVINL float block_reduce(float v, float* sh, bool is_max) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : v + t;
+  }
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float x = lane < (blockDim.x >> 5) ? sh[lane] : (is_max ? -INFINITY : 0.f);
+    for (int o = 16; o > 0; o >>= 1) {
+      const float t = __shfl_xor_sync(0xffffffffu, x, o);
+      x = is_max ? fmaxf(x, t) : x + t;
+    }
+    if (lane == 0) sh[0] = x;
+  }
+  __syncthreads();
+  return sh[0];
+}
+
+__global__ void __launch_bounds__(kNceThreads) nce_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                              const float* __restrict__ queue, float T, int B, int D,
+                                                              int K, float* __restrict__ logits,
+                                                              float* __restrict__ loss_rows,
+                                                              float* __restrict__ dlogits) {
+  extern __shared__ float sm[];
+  float* sq = sm;        // [D]
+  float* red = sm + D;   // [32]
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) sq[c] = q[(long)b * D + c];
+  __syncthreads();
+  float* lrow = logits + (long)b * (K + 1);
+  // positive logit
+  float pp = 0.f;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) pp += sq[c] * k[(long)b * D + c];
+  const float lpos = block_reduce(pp, red, false) / T;
+  if (threadIdx.x == 0) lrow[0] = lpos;
+  float mx = lpos;
+  for (int j = threadIdx.x; j < K; j += blockDim.x) {
+    float a = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < D; ++c) a = fmaf(sq[c], __ldg(queue + (long)c * K + j), a);
+    a = a / T;
+    lrow[1 + j] = a;
+    mx = fmaxf(mx, a);
+  }
+  mx = block_reduce(mx, red, true);
+  float se = 0.f;
+  for (int j = threadIdx.x; j < K + 1; j += blockDim.x) se += __expf(lrow[j] - mx);  // own writes / thread 0's lpos
+  __syncthreads();
+  se = block_reduce(se, red, false);
+  const float lse = mx + logf(se);
+  if (threadIdx.x == 0 && loss_rows) loss_rows[b] = lse - lpos;
+  if (dlogits) {
+    const float invB = 1.f / (float)B;
+    float* drow = dlogits + (long)b * (K + 1);
+    for (int j = threadIdx.x; j < K + 1; j += blockDim.x) {
+      const float p = __expf(lrow[j] - lse);
+      drow[j] = (p - (j == 0 ? 1.f : 0.f)) * invB;
+    }
+  }
+}
+
+// dq[b, c] = ( dlogits[b,0] * k[b,c] + sum_j dlogits[b,1+j] * queue[c, j] ) / T
+__global__ void __launch_bounds__(kNceThreads) nce_bwd_kernel(const float* __restrict__ dlogits,
+                                                              const float* __restrict__ k,
+                                                              const float* __restrict__ queue, float T, int D, int K,
+                                                              float* __restrict__ dq) {
+  extern __shared__ float sd[];  // [K+1]
+  const int b = blockIdx.x;
+  for (int j = threadIdx.x; j < K + 1; j += blockDim.x) sd[j] = dlogits[(long)b * (K + 1) + j];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = w; c < D; c += nw) {
+    float a = 0.f;
+    for (int j = lane; j < K; j += 32) a = fmaf(sd[1 + j], __ldg(queue + (long)c * K + j), a);
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) dq[(long)b * D + c] = (a + sd[0] * k[(long)b * D + c]) / T;
+  }
+}
+
+}  // namespace coclr
+
+using namespace coclr;
+
+extern "C" int coclr_nce_logits_ce(const float* q, const float* k, const float* queue, float T, int B, int D, int K,
+                                   float* logits, float* loss_rows, float* dlogits, coclr_stream_t stream) {
+  if (!q || !k || !queue || !logits || B <= 0 || D <= 0 || K <= 0) return COCLR_E_ARG;
+  nce_fwd_kernel<<<B, kNceThreads, (D + 32) * sizeof(float), (cudaStream_t)stream>>>(q, k, queue, T, B, D, K, logits,
+                                                                                    loss_rows, dlogits);
+  return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
+}
+
+extern "C" int coclr_nce_logits_bwd(const float* dlogits, const float* k, const float* queue, float T, int B, int D,
+                                    int K, float* dq, coclr_stream_t stream) {
+  if (!dlogits || !k || !queue || !dq) return COCLR_E_ARG;
+  const size_t smem = (size_t)(K + 1) * sizeof(float);
+  if (smem > 200 * 1024) return COCLR_E_ARG;
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(nce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return COCLR_E_LAUNCH;
+  }
+  nce_bwd_kernel<<<B, kNceThreads, smem, (cudaStream_t)stream>>>(dlogits, k, queue, T, D, K, dq);
+  return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
+}

@@ -1,0 +1,537 @@
+"""Host-side executor of one encoder (S3D backbone + MoCo projection head) on the sm_100a kernels.
+
+The reference runs `encoder_q(x1)` / `encoder_k(x2)` (model/pretrain.py:153,165) as ~250 PyTorch
+module calls; here an encoder pass is a pre-built list of C-ABI kernel launches over pre-allocated
+channels-last buffers:
+
+  clip pack -> [conv (+BN statistics in the epilogue) -> BN finalize]* with BN-apply/ReLU folded into
+  the next operand load, max-pools, concat-by-slice -> avg-pool -> 2 head convs -> L2-normalise
+
+and the backward pass is the mirrored list (BN backward in place, dgrad, wgrad into one flat
+gradient buffer).  Parameters live in ONE flat fp32 buffer per encoder (nn.Parameters are views), so
+EMA / Adam / all-reduce are single launches over it.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+from . import ops
+from .s3d_spec import s3d_stages, S3D_FEATURE_SIZE
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+# name -> (fwd_npass, fwd_bf16, bwd_npass, bwd_bf16)
+PRECISIONS = {
+    "parity": (3, 0, 3, 1),   # fp16 hi/lo split forward (fp32-grade), bf16 hi/lo split backward
+    "fast": (1, 1, 1, 1),     # single-pass bf16 everywhere (does NOT meet the 1e-3 parity bar)
+    "mixed": (3, 0, 1, 1),    # fp32-grade forward, single-pass bf16 backward
+}
+
+
+def _round4(c):
+    return (c + 3) // 4 * 4
+
+
+# ---------------------------------------------------------------------------------------------
+# symbolic graph
+# ---------------------------------------------------------------------------------------------
+class TensorSpec:
+    def __init__(self, name, C, dims_fn, pending):
+        self.name, self.C, self.dims_fn, self.pending = name, C, dims_fn, pending
+        self.bn_members = []   # (bn module name, coff, C) in channel order
+        self.relu = 1 if pending else 0
+
+
+class ConvSpec:
+    def __init__(self, name, src, dst, dst_coff, cin, cout, k, s, p, bias=None, need_dgrad=True):
+        self.name, self.src, self.dst, self.dst_coff = name, src, dst, dst_coff
+        self.cin, self.cout, self.k, self.s, self.p = cin, cout, k, s, p
+        self.bias, self.need_dgrad = bias, need_dgrad
+
+
+class PoolSpec:
+    def __init__(self, name, src, dst, k, s, p):
+        self.name, self.src, self.dst, self.k, self.s, self.p = name, src, dst, k, s, p
+
+
+def _conv_out(d, k, s, p):
+    return (d + 2 * p - k) // s + 1
+
+
+class Graph:
+    """Shape-independent description of the encoder: tensors, convs, pools in forward order."""
+
+    def __init__(self, stages, first_channel=3, head_dim=None, feature_size=S3D_FEATURE_SIZE, bb_prefix=""):
+        self.tensors, self.items = [], []   # items: ("conv", ConvSpec) | ("pool", PoolSpec) | ("bn", TensorSpec)
+        self.first_channel = first_channel
+        self.head_dim, self.feature_size = head_dim, feature_size
+        pre = bb_prefix
+        x = self._tensor("input", _round4(first_channel), lambda d: d, pending=False)
+        self.input = x
+        first_conv = True
+        for stg in stages:
+            kind = stg[0]
+            if kind == "st":
+                _, name, cin, cout, k, ss, ts, pad = stg
+                x = self._st(pre + name, x, None, 0, cin, cout, k, ss, ts, pad, need_dgrad=not first_conv)
+                first_conv = False
+            elif kind == "basic":
+                _, name, cin, cout = stg
+                y = self._tensor(pre + name, cout, self._same(x))
+                self._conv(pre + name + ".conv", x, y, 0, cin, cout, (1, 1, 1), (1, 1, 1), (0, 0, 0))
+                y.bn_members.append((pre + name + ".bn", 0, cout))
+                self.items.append(("bn", y))
+                x = y
+            elif kind == "pool":
+                _, name, k, s, p = stg
+                x = self._pool(pre + name, x, k, s, p)
+            elif kind == "mixed":
+                _, name, cin, planes = stg
+                x = self._mixed(pre + name, x, cin, planes)
+            else:
+                raise ValueError(kind)
+        self.backbone_out = x
+
+    # -- helpers --
+    def _tensor(self, name, C, dims_fn, pending=True):
+        t = TensorSpec(name, C, dims_fn, pending)
+        t.index = len(self.tensors)
+        self.tensors.append(t)
+        return t
+
+    @staticmethod
+    def _same(src):
+        return src.dims_fn
+
+    @staticmethod
+    def _after(src, k, s, p):
+        f = src.dims_fn
+        return lambda d: tuple(_conv_out(v, kk, ss, pp) for v, kk, ss, pp in zip(f(d), k, s, p))
+
+    def _conv(self, name, src, dst, dst_coff, cin, cout, k, s, p, need_dgrad=True):
+        c = ConvSpec(name, src, dst, dst_coff, cin, cout, k, s, p, need_dgrad=need_dgrad)
+        self.items.append(("conv", c))
+        return c
+
+    def _st(self, name, x, dst, dst_coff, cin, cout, k, ss, ts, pad, need_dgrad=True):
+        k1, s1, p1 = (1, k, k), (1, ss, ss), (0, pad, pad)
+        k2, s2, p2 = (k, 1, 1), (ts, 1, 1), (pad, 0, 0)
+        mid = self._tensor(name + ".mid", cout, self._after(x, k1, s1, p1))
+        self._conv(name + ".conv1", x, mid, 0, cin, cout, k1, s1, p1, need_dgrad=need_dgrad)
+        mid.bn_members.append((name + ".bn1", 0, cout))
+        self.items.append(("bn", mid))
+        own = dst is None
+        if own:
+            dst = self._tensor(name, cout, self._after(mid, k2, s2, p2))
+        self._conv(name + ".conv2", mid, dst, dst_coff, cout, cout, k2, s2, p2)
+        dst.bn_members.append((name + ".bn2", dst_coff, cout))
+        if own:
+            self.items.append(("bn", dst))
+        return dst
+
+    def _pool(self, name, x, k, s, p):
+        y = self._tensor(name, x.C, self._after(x, k, s, p), pending=False)
+        self.items.append(("pool", PoolSpec(name, x, y, k, s, p)))
+        return y
+
+    def _mixed(self, name, x, cin, planes):
+        o0, o1a, o1b, o2a, o2b, o3b = planes
+        cat = self._tensor(name, o0 + o1b + o2b + o3b, self._same(x))
+        one = ((1, 1, 1), (1, 1, 1), (0, 0, 0))
+        self._conv(name + ".branch0.0.conv", x, cat, 0, cin, o0, *one)
+        cat.bn_members.append((name + ".branch0.0.bn", 0, o0))
+        t1 = self._tensor(name + ".b1a", o1a, self._same(x))
+        self._conv(name + ".branch1.0.conv", x, t1, 0, cin, o1a, *one)
+        t1.bn_members.append((name + ".branch1.0.bn", 0, o1a))
+        self.items.append(("bn", t1))
+        self._st(name + ".branch1.1", t1, cat, o0, o1a, o1b, 3, 1, 1, 1)
+        t2 = self._tensor(name + ".b2a", o2a, self._same(x))
+        self._conv(name + ".branch2.0.conv", x, t2, 0, cin, o2a, *one)
+        t2.bn_members.append((name + ".branch2.0.bn", 0, o2a))
+        self.items.append(("bn", t2))
+        self._st(name + ".branch2.1", t2, cat, o0 + o1b, o2a, o2b, 3, 1, 1, 1)
+        tp = self._pool(name + ".branch3.0", x, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+        self._conv(name + ".branch3.1.conv", tp, cat, o0 + o1b + o2b, cin, o3b, *one)
+        cat.bn_members.append((name + ".branch3.1.bn", o0 + o1b + o2b, o3b))
+        self.items.append(("bn", cat))
+        return cat
+
+    # -- parameter inventory (names relative to the encoder: backbone under bb_prefix, head '2.', '4.') --
+    def param_layout(self):
+        """[(name, shape)] in flat-buffer order; BN members of one tensor are contiguous (all gammas, then
+        all betas) so that BatchNorm kernels address a whole concat buffer at once."""
+        out = []
+        for kind, it in self.items:
+            if kind == "conv":
+                out.append((it.name + ".weight", (it.cout, it.cin) + tuple(it.k)))
+        for kind, it in self.items:
+            if kind == "bn":
+                for nm, _, c in it.bn_members:
+                    out.append((nm + ".weight", (c,)))
+                for nm, _, c in it.bn_members:
+                    out.append((nm + ".bias", (c,)))
+        if self.head_dim is not None:
+            fs = self.feature_size
+            out += [("2.weight", (fs, fs, 1, 1, 1)), ("2.bias", (fs,)),
+                    ("4.weight", (self.head_dim, fs, 1, 1, 1)), ("4.bias", (self.head_dim,))]
+        return out
+
+    def buffer_layout(self):
+        """[(name, C)] for running_mean (same order for running_var), tensor-contiguous."""
+        out = []
+        for kind, it in self.items:
+            if kind == "bn":
+                for nm, _, c in it.bn_members:
+                    out.append((nm, c))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# flat parameter storage
+# ---------------------------------------------------------------------------------------------
+class ParamStore:
+    """One flat fp32 buffer for all parameters of an encoder (+ flat grad, flat BN running stats)."""
+
+    def __init__(self, graph, device):
+        self.graph, self.device = graph, device
+        self.offsets = {}
+        off = 0
+        for name, shape in graph.param_layout():
+            n = 1
+            for s in shape:
+                n *= s
+            self.offsets[name] = (off, n, shape)
+            off += (n + 3) // 4 * 4
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+        self.buf_offsets = {}
+        boff = 0
+        for name, c in graph.buffer_layout():
+            self.buf_offsets[name] = (boff, c)
+            boff += c
+        self.running_mean = torch.zeros(boff, dtype=torch.float32, device=device)
+        self.running_var = torch.ones(boff, dtype=torch.float32, device=device)
+        self.nbt = torch.zeros(len(self.buf_offsets), dtype=torch.long, device=device)
+        self.nbt_index = {name: i for i, name in enumerate(self.buf_offsets)}
+
+    def view(self, name, grad=False):
+        off, n, shape = self.offsets[name]
+        return (self.grad if grad else self.flat)[off:off + n].view(shape)
+
+    def bind_module(self, named_params, named_buffers, prefix_map=lambda n: n):
+        """Copy the module's current values in and rebind every Parameter / BN buffer to a view."""
+        with torch.no_grad():
+            for name in self.offsets:
+                p = named_params[prefix_map(name)]
+                v = self.view(name)
+                v.copy_(p.detach().to(self.device))
+                p.data = v
+                p.grad = None
+            nbt_host = []
+            for name, (boff, c) in self.buf_offsets.items():
+                for suffix, flat in ((".running_mean", self.running_mean), (".running_var", self.running_var)):
+                    b = named_buffers[prefix_map(name + suffix)]
+                    assert b.device == flat.device, "move the module to the CUDA device before the first forward"
+                    v = flat[boff:boff + c]
+                    v.copy_(b)
+                    b.set_(v.untyped_storage(), v.storage_offset(), v.shape, v.stride())
+                nbt_host.append(named_buffers[prefix_map(name + ".num_batches_tracked")])
+            self.nbt.copy_(torch.stack([t.detach().reshape(()) for t in nbt_host]).to(self.nbt.device))
+            for i, nb in enumerate(nbt_host):
+                nb.set_(self.nbt.untyped_storage(), i, (), ())
+
+    def attach_grads(self, named_params, prefix_map=lambda n: n):
+        for name in self.offsets:
+            p = named_params[prefix_map(name)]
+            if p.requires_grad:
+                p.grad = self.view(name, grad=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# shape-specific plan
+# ---------------------------------------------------------------------------------------------
+class _Act:
+    __slots__ = ("spec", "dims", "data", "grad", "scale", "shift", "mean", "rstd", "ssum", "ssq", "idx", "bsums",
+                 "grad_written", "M")
+
+
+class Plan:
+    """Buffers + launch lists for one (B, T, H, W, training) configuration."""
+
+    def __init__(self, eng, B, T, H, W, training, with_backward):
+        self.eng, self.B, self.dims0, self.training, self.with_backward = eng, B, (T, H, W), training, with_backward
+        g, dev = eng.graph, eng.store.device
+        lib = L.load()
+        self.keep = []          # keeps ctypes structs / tensors alive
+        self.fwd, self.bwd = [], []
+        nsm = L.num_sms(dev)
+        fnp, fbf, bnp, bbf = PRECISIONS[eng.precision]
+        # ---- activations ----
+        acts = {}
+        n_stat = sum(t.C for t in g.tensors if t.pending)
+        self.stats = torch.zeros(2 * n_stat, dtype=torch.float64, device=dev)
+        self.aff = torch.zeros(4 * n_stat, dtype=torch.float32, device=dev)  # scale, shift, mean, rstd
+        so = 0
+        for t in g.tensors:
+            a = _Act()
+            a.spec, a.dims = t, t.dims_fn((T, H, W))
+            a.M = B * a.dims[0] * a.dims[1] * a.dims[2]
+            a.data = torch.empty((B,) + a.dims + (t.C,), dtype=torch.float32, device=dev)
+            a.grad, a.idx, a.bsums, a.grad_written = None, None, None, False
+            if t.pending:
+                a.ssum = self.stats[so:so + t.C]
+                a.ssq = self.stats[n_stat + so:n_stat + so + t.C]
+                a.scale = self.aff[so:so + t.C]
+                a.shift = self.aff[n_stat + so:n_stat + so + t.C]
+                a.mean = self.aff[2 * n_stat + so:2 * n_stat + so + t.C]
+                a.rstd = self.aff[3 * n_stat + so:3 * n_stat + so + t.C]
+                so += t.C
+            else:
+                a.ssum = a.ssq = a.scale = a.shift = a.mean = a.rstd = None
+            if with_backward and t is not g.input:
+                a.grad = torch.empty_like(a.data)
+            acts[t.index] = a
+        self.acts = acts
+        self.input = acts[g.input.index]
+        st = eng.store
+
+        def src_of(a, C=None, grad=False):
+            sp = a.spec
+            return ops.make_src(a.grad if grad else a.data, 0, C or sp.C, a.dims[0], a.dims[1], a.dims[2],
+                                None if grad else a.scale, None if grad else a.shift,
+                                relu=(sp.relu and not grad))
+
+        # ---- forward ----
+        for kind, it in g.items:
+            if kind == "conv":
+                sa, da = acts[it.src.index], acts[it.dst.index]
+                geom = ops.Geometry(it.k, it.s, it.p)
+                pw = eng.packed_fwd[it.name]
+                cv = ops.make_conv(src_of(sa), geom.c(0), B, da.dims, pw, da.data, it.dst_coff,
+                                   stats_sum=da.ssum[it.dst_coff:] if training else None,
+                                   stats_sq=da.ssq[it.dst_coff:] if training else None, npass=fnp)
+                self.keep.append(cv)
+                self.fwd.append((lib.coclr_conv_igemm, (C.byref(cv), nsm)))
+            elif kind == "pool":
+                sa, da = acts[it.src.index], acts[it.dst.index]
+                geom = ops.Geometry(it.k, it.s, it.p)
+                if with_backward:
+                    da.idx = torch.empty(da.M * it.dst.C, dtype=torch.uint8, device=dev)
+                pl = L.Pool(L.dptr(sa.data), it.src.C, 0, L.dptr(sa.scale), L.dptr(sa.shift), it.src.relu,
+                            L.dptr(da.data), it.dst.C, 0, L.dptr(da.idx), B, it.dst.C,
+                            sa.dims[0], sa.dims[1], sa.dims[2], da.dims[0], da.dims[1], da.dims[2], geom.c(0),
+                            None, None, 0)
+                self.keep.append(pl)
+                self.fwd.append((lib.coclr_maxpool_fwd, (C.byref(pl),)))
+            elif kind == "bn":
+                a = acts[it.index]
+                first = it.bn_members[0][0]
+                goff = st.offsets[first + ".weight"][0]
+                boff_b = st.offsets[first + ".bias"][0]
+                rboff = st.buf_offsets[first][0]
+                bf = L.BnFinalize(L.dptr(a.ssum), L.dptr(a.ssq), a.M,
+                                  L.dptr(st.flat[goff:]), L.dptr(st.flat[boff_b:]),
+                                  L.dptr(st.running_mean[rboff:]), L.dptr(st.running_var[rboff:]),
+                                  BN_MOMENTUM, BN_EPS, int(training), L.dptr(a.scale), L.dptr(a.shift),
+                                  L.dptr(a.mean), L.dptr(a.rstd), it.C)
+                self.keep.append(bf)
+                self.fwd.append((lib.coclr_bn_finalize, (C.byref(bf),)))
+        # ---- head ----
+        out = acts[g.backbone_out.index]
+        self.backbone_out = out
+        if g.head_dim is not None:
+            fs, hd = g.feature_size, g.head_dim
+            Pn = out.dims[0] * out.dims[1] * out.dims[2]
+            self.feat = torch.empty(B, 1, 1, 1, fs, dtype=torch.float32, device=dev)
+            self.h1 = torch.empty(B, 1, 1, 1, fs, dtype=torch.float32, device=dev)
+            self.h2 = torch.empty(B, 1, 1, 1, hd, dtype=torch.float32, device=dev)
+            self.q = torch.empty(B, hd, dtype=torch.float32, device=dev)
+            self.inv_norm = torch.empty(B, dtype=torch.float32, device=dev)
+            self.ones = torch.ones(fs, dtype=torch.float32, device=dev)
+            self.fwd.append((lib.coclr_avgpool_fwd, (L.dptr(out.data), out.spec.C, 0, L.dptr(out.scale), L.dptr(out.shift),
+                                                     out.spec.relu, L.dptr(self.feat), B, Pn, fs)))
+            one = ops.Geometry((1, 1, 1))
+            s_feat = ops.make_src(self.feat, 0, fs, 1, 1, 1)
+            b2, b4 = st.view("2.bias"), st.view("4.bias")
+            s_h1 = ops.make_src(self.h1, 0, fs, 1, 1, 1, self.ones, b2, relu=True)
+            c1 = ops.make_conv(s_feat, one.c(0), B, (1, 1, 1), eng.packed_fwd["2"], self.h1, npass=fnp)
+            c2 = ops.make_conv(s_h1, one.c(0), B, (1, 1, 1), eng.packed_fwd["4"], self.h2, npass=fnp)
+            self.keep += [c1, c2, s_feat, s_h1]
+            self.fwd.append((lib.coclr_conv_igemm, (C.byref(c1), nsm)))
+            self.fwd.append((lib.coclr_conv_igemm, (C.byref(c2), nsm)))
+            self.fwd.append((lib.coclr_l2norm_fwd, (L.dptr(self.h2), L.dptr(b4), L.dptr(self.q), L.dptr(self.inv_norm), B, hd)))
+        if not with_backward:
+            return
+        # ---- backward ----
+        bw = self.bwd
+        if g.head_dim is not None:
+            self.dq = torch.empty(B, hd, dtype=torch.float32, device=dev)
+            self.dh2 = torch.empty(B, 1, 1, 1, hd, dtype=torch.float32, device=dev)
+            self.dh1 = torch.empty(B, 1, 1, 1, fs, dtype=torch.float32, device=dev)
+            self.dfeat = torch.empty(B, 1, 1, 1, fs, dtype=torch.float32, device=dev)
+            bw.append((lib.coclr_l2norm_bwd, (L.dptr(self.q), L.dptr(self.dq), L.dptr(self.inv_norm), L.dptr(self.dh2),
+                                              L.dptr(st.view("4.bias", grad=True)), B, hd)))
+            s_dh2 = ops.make_src(self.dh2, 0, hd, 1, 1, 1)
+            wg2 = L.Wgrad(s_h1, one.c(0), s_dh2, B, 1, 1, 1, hd, fs, L.dptr(st.view("4.weight", grad=True)), bnp, bbf, 1)
+            dg2 = ops.make_conv(s_dh2, one.c(1), B, (1, 1, 1), eng.packed_bwd["4"], self.dh1, npass=bnp)
+            s_dh1 = ops.make_src(self.dh1, 0, fs, 1, 1, 1)
+            wg1 = L.Wgrad(s_feat, one.c(0), s_dh1, B, 1, 1, 1, fs, fs, L.dptr(st.view("2.weight", grad=True)), bnp, bbf, 1)
+            dg1 = ops.make_conv(s_dh1, one.c(1), B, (1, 1, 1), eng.packed_bwd["2"], self.dfeat, npass=bnp)
+            self.keep += [s_dh2, wg2, dg2, s_dh1, wg1, dg1]
+            bw.append((lib.coclr_conv_wgrad, (C.byref(wg2),)))
+            bw.append((lib.coclr_conv_igemm, (C.byref(dg2), nsm)))
+            bw.append((lib.coclr_bias_relu_bwd, (L.dptr(self.h1), L.dptr(b2), L.dptr(self.dh1),
+                                                 L.dptr(st.view("2.bias", grad=True)), B, fs)))
+            bw.append((lib.coclr_conv_wgrad, (C.byref(wg1),)))
+            bw.append((lib.coclr_conv_igemm, (C.byref(dg1), nsm)))
+            bw.append((lib.coclr_avgpool_bwd, (L.dptr(self.dfeat), L.dptr(out.grad), out.spec.C, 0, B, Pn, fs)))
+            out.grad_written = True
+        # tensors in reverse creation order; each pushes gradient into its producers' sources
+        convs_into, pool_into = {}, {}
+        for kind, it in g.items:
+            if kind == "conv":
+                convs_into.setdefault(it.dst.index, []).append(it)
+            elif kind == "pool":
+                pool_into[it.dst.index] = it
+        for t in reversed(g.tensors):
+            a = acts[t.index]
+            if t is g.input:
+                continue
+            if not a.grad_written:
+                raise RuntimeError("tensor %s never receives a gradient" % t.name)
+            if t.pending:
+                a.bsums = torch.zeros(2 * t.C, dtype=torch.float64, device=dev)
+                first = t.bn_members[0][0]
+                goff = st.offsets[first + ".weight"][0]
+                boff_b = st.offsets[first + ".bias"][0]
+                bb = L.BnBwd(L.dptr(a.data), L.dptr(a.grad), t.C, 0, t.C, a.M, L.dptr(a.scale), L.dptr(a.shift),
+                             L.dptr(a.mean), L.dptr(a.rstd), t.relu, L.dptr(a.bsums),
+                             L.dptr(st.grad[goff:]), L.dptr(st.grad[boff_b:]))
+                self.keep.append(bb)
+                bw.append((lib.coclr_bn_bwd, (C.byref(bb), nsm)))
+                for it in convs_into[t.index]:
+                    sa = acts[it.src.index]
+                    geom = ops.Geometry(it.k, it.s, it.p)
+                    cin_p = it.src.C
+                    dy = ops.make_src(a.grad, it.dst_coff, _round4(it.cout), a.dims[0], a.dims[1], a.dims[2])
+                    taps = geom.taps
+                    # pixel splits so that the grid roughly fills the device
+                    kreal = taps * cin_p
+                    bnk = min(256, ((kreal + ((kreal + 255) // 256) - 1) // ((kreal + 255) // 256) + 63) // 64 * 64)
+                    tiles = ((kreal + bnk - 1) // bnk) * ((it.cout + 127) // 128)
+                    chunks = (a.M + 63) // 64
+                    splits = max(1, min(chunks, (2 * nsm + tiles - 1) // tiles))
+                    wg = L.Wgrad(src_of(sa), geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin,
+                                 L.dptr(st.view(it.name + ".weight", grad=True)), bnp, bbf, splits)
+                    self.keep += [wg, dy]
+                    bw.append((lib.coclr_conv_wgrad, (C.byref(wg),)))
+                    if it.need_dgrad:
+                        dg = ops.make_conv(dy, geom.c(1), B, sa.dims, eng.packed_bwd[it.name], sa.grad, 0,
+                                           accumulate=sa.grad_written, npass=bnp)
+                        self.keep.append(dg)
+                        bw.append((lib.coclr_conv_igemm, (C.byref(dg), nsm)))
+                        sa.grad_written = True
+            elif t.index in pool_into:
+                it = pool_into[t.index]
+                sa = acts[it.src.index]
+                geom = ops.Geometry(it.k, it.s, it.p)
+                pl = L.Pool(L.dptr(sa.data), it.src.C, 0, None, None, 0,
+                            L.dptr(a.data), t.C, 0, L.dptr(a.idx), B, t.C,
+                            sa.dims[0], sa.dims[1], sa.dims[2], a.dims[0], a.dims[1], a.dims[2], geom.c(0),
+                            L.dptr(a.grad), L.dptr(sa.grad), int(sa.grad_written))
+                self.keep.append(pl)
+                bw.append((lib.coclr_maxpool_bwd, (C.byref(pl),)))
+                sa.grad_written = True
+
+
+class EncoderEngine:
+    """Executes one encoder (see module docstring)."""
+
+    def __init__(self, store, graph, precision="parity"):
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % list(PRECISIONS))
+        self.store, self.graph, self.precision = store, graph, precision
+        self.plans = {}
+        dev = store.device
+        fnp, fbf, bnp, bbf = PRECISIONS[precision]
+        self.packed_fwd, self.packed_bwd, self._packs = {}, {}, []
+        for kind, it in graph.items:
+            if kind != "conv":
+                continue
+            taps = it.k[0] * it.k[1] * it.k[2]
+            w = store.view(it.name + ".weight")
+            pf = ops.PackedWeights(it.cout, it.cin, taps, it.src.C, 0, fbf, dev)
+            self.packed_fwd[it.name] = pf
+            self._packs.append((pf, w, False))
+            if it.need_dgrad:
+                pb = ops.PackedWeights(it.cout, it.cin, taps, _round4(it.cout), 1, bbf, dev)
+                self.packed_bwd[it.name] = pb
+                self._packs.append((pb, w, True))
+        if graph.head_dim is not None:
+            fs, hd = graph.feature_size, graph.head_dim
+            for nm, co in (("2", fs), ("4", hd)):
+                w = store.view(nm + ".weight")
+                pf = ops.PackedWeights(co, fs, 1, fs, 0, fbf, dev)
+                pb = ops.PackedWeights(co, fs, 1, _round4(co), 1, bbf, dev)
+                self.packed_fwd[nm], self.packed_bwd[nm] = pf, pb
+                self._packs += [(pf, w, False), (pb, w, True)]
+
+    def pack_weights(self, backward=True):
+        """Re-derive the 16-bit hi/lo tile images from the current fp32 weights."""
+        for pw, w, is_bwd in self._packs:
+            if is_bwd and not backward:
+                continue
+            pw.pack(w)
+
+    def plan(self, B, T, H, W, training, with_backward):
+        key = (B, T, H, W, bool(training), bool(with_backward))
+        p = self.plans.get(key)
+        if p is None:
+            p = Plan(self, B, T, H, W, training, with_backward)
+            self.plans[key] = p
+        return p
+
+    @staticmethod
+    def _run(oplist):
+        stream = L.stream_ptr()
+        for fn, args in oplist:
+            rc = fn(*args, stream)
+            if rc != 0:
+                raise L.CoclrError("%s failed with code %d" % (fn.__name__, rc))
+
+    def forward(self, x, training=True, with_backward=False, repack=True, batch_index=None, batch=None):
+        """x: [*, C, T, H, W] fp32 CUDA (any batch stride). Clip b of the pass is x[batch_index[b]] when a
+        device int64 index is given (shuffle-BN gather), else x[b].  Returns the plan; plan.q holds the
+        normalised features [B, dim] (plan.backbone_out the raw backbone output when there is no head)."""
+        if not x.is_cuda:
+            raise L.CoclrError("coclr_b200 encoders run on CUDA only (no CPU fallback)")
+        _, Cin, T, H, W = x.shape
+        B = x.shape[0] if batch is None else batch
+        assert Cin == self.graph.first_channel and x.dtype == torch.float32
+        assert x.stride(4) == 1 and x.stride(3) == W and x.stride(2) == H * W and x.stride(1) == T * H * W
+        if batch_index is not None:
+            assert batch_index.dtype == torch.long and batch_index.is_cuda and batch_index.numel() == B
+        p = self.plan(B, T, H, W, training, with_backward)
+        if repack:
+            self.pack_weights(backward=with_backward)
+        if training:
+            p.stats.zero_()
+            self.store.nbt += 1
+        lib = L.load()
+        L.check(lib.coclr_pack_input(L.dptr(x), x.stride(0), x.stride(1), Cin, L.dptr(p.input.data), B, T * H * W,
+                                     L.dptr(batch_index), L.stream_ptr()), "coclr_pack_input")
+        self._run(p.fwd)
+        return p
+
+    def backward(self, p, dq):
+        """dq: gradient w.r.t. the normalised features [B, dim]; accumulates into store.grad."""
+        p.dq.copy_(dq)
+        self._run(p.bwd)
+
+    def backbone_output_ncdhw(self, p):
+        a = p.backbone_out
+        y = torch.relu(a.data * a.scale + a.shift)
+        return y.permute(0, 4, 1, 2, 3).contiguous()

@@ -36,7 +36,7 @@ class Conv(C.Structure):
                 ("Kreal", C.c_int), ("wpk", C.c_void_p), ("wunscale", C.c_void_p),
                 ("N", C.c_int), ("BN", C.c_int), ("n_tiles", C.c_int),
                 ("dst", C.c_void_p), ("dst_ld", C.c_int), ("dst_coff", C.c_int),
-                ("accumulate", C.c_int), ("stats", C.c_void_p),
+                ("accumulate", C.c_int), ("stats_sum", C.c_void_p), ("stats_sq", C.c_void_p),
                 ("npass", C.c_int), ("bf16", C.c_int)]
 
 
@@ -51,6 +51,38 @@ class Pack(C.Structure):
     _fields_ = [("w", C.c_void_p), ("Cout", C.c_int), ("Cin", C.c_int), ("taps", C.c_int),
                 ("Cpad", C.c_int), ("mode", C.c_int), ("bf16", C.c_int),
                 ("wpk", C.c_void_p), ("unscale", C.c_void_p)]
+
+
+class BnFinalize(C.Structure):
+    _fields_ = [("sum", C.c_void_p), ("sumsq", C.c_void_p), ("count", C.c_long),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+                ("momentum", C.c_float), ("eps", C.c_float), ("training", C.c_int),
+                ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("save_mean", C.c_void_p), ("save_rstd", C.c_void_p), ("C", C.c_int)]
+
+
+class BnBwd(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("dA", C.c_void_p), ("ld", C.c_int), ("coff", C.c_int), ("C", C.c_int),
+                ("M", C.c_long), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("mean", C.c_void_p), ("rstd", C.c_void_p), ("relu", C.c_int),
+                ("sums", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p)]
+
+
+class Pool(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("ldx", C.c_int), ("x_coff", C.c_int),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int),
+                ("y", C.c_void_p), ("ldy", C.c_int), ("y_coff", C.c_int), ("idx", C.c_void_p),
+                ("B", C.c_int), ("C", C.c_int), ("Ti", C.c_int), ("Hi", C.c_int), ("Wi", C.c_int),
+                ("To", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int), ("g", Geom),
+                ("dy", C.c_void_p), ("dx", C.c_void_p), ("accumulate", C.c_int)]
+
+
+class Adam(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n", C.c_long), ("grad_scale", C.c_float),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("step_size", C.c_float), ("bc2_sqrt", C.c_float)]
 
 
 def library_path():

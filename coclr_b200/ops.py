@@ -58,12 +58,18 @@ class PackedWeights:
         return self
 
 
+def make_conv(src, geom_c, B, dst_dims, pw, dst, dst_coff=0, accumulate=False, stats_sum=None, stats_sq=None, npass=3):
+    Td, Hd, Wd = dst_dims
+    return L.Conv(src, geom_c, B, Td, Hd, Wd, pw.Kreal, L.dptr(pw.wpk), L.dptr(pw.unscale),
+                  pw.N, pw.BN, pw.n_tiles, L.dptr(dst), dst.shape[-1], dst_coff, int(bool(accumulate)),
+                  L.dptr(stats_sum), L.dptr(stats_sq), npass, pw.bf16)
+
+
 def conv_igemm(src, geom_c, B, dst_dims, pw, dst, dst_coff=0, accumulate=False, stats=None, npass=3):
     """Run the implicit-GEMM conv. src: L.Src; geom_c: L.Geom; dst: [B,Td,Hd,Wd,ld] fp32."""
-    Td, Hd, Wd = dst_dims
-    p = L.Conv(src, geom_c, B, Td, Hd, Wd, pw.Kreal, L.dptr(pw.wpk), L.dptr(pw.unscale),
-               pw.N, pw.BN, pw.n_tiles, L.dptr(dst), dst.shape[-1], dst_coff, int(bool(accumulate)),
-               L.dptr(stats), npass, pw.bf16)
+    ssum = stats[:pw.N] if stats is not None else None
+    ssq = stats[pw.N:] if stats is not None else None
+    p = make_conv(src, geom_c, B, dst_dims, pw, dst, dst_coff, accumulate, ssum, ssq, npass)
     L.check(L.load().coclr_conv_igemm(C.byref(p), L.num_sms(), L.stream_ptr()), "coclr_conv_igemm")
 
 

@@ -63,7 +63,8 @@ typedef struct {
   float* dst;
   int dst_ld, dst_coff;
   int accumulate;  /* dst += result */
-  double* stats;   /* [2*N]: sum, then sum of squares; NULL to skip */
+  double* stats_sum; /* [N] per-output-channel sum of Y, accumulated (zero it first); NULL to skip */
+  double* stats_sq;  /* [N] per-output-channel sum of Y*Y */
   int npass;       /* 1 = single 16-bit pass, 3 = hi/lo split (fp32-equivalent) */
   int bf16;        /* 0 = fp16 operands, 1 = bf16 operands */
 } coclr_conv_t;
@@ -99,6 +100,115 @@ typedef struct {
   float* unscale; /* [n_tiles*BN] */
 } coclr_pack_t;
 int coclr_pack_weights(const coclr_pack_t* p, coclr_stream_t stream);
+
+/* ---- BatchNorm3d (train mode; backbone/s3dg.py:16,46-47) ------------------------------------------
+ * finalize: per-channel sums written by coclr_conv_igemm -> (scale, shift) consumed by the next
+ * operand load, saved (mean, rstd) for backward, running-stat momentum update (unbiased variance).
+ * training == 0: scale/shift from the running statistics (eval-mode BN, main_coclr.py:363). */
+typedef struct {
+  const double* sum;
+  const double* sumsq;
+  long count; /* B*T*H*W */
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float momentum, eps;
+  int training;
+  float* scale;
+  float* shift;
+  float* save_mean; /* may be NULL */
+  float* save_rstd;
+  int C;
+} coclr_bn_finalize_t;
+int coclr_bn_finalize(const coclr_bn_finalize_t* p, coclr_stream_t stream);
+
+/* backward of BatchNorm+ReLU, in place: dA (grad w.r.t. relu(bn(y))) -> dY (grad w.r.t. y);
+ * also dgamma / dbeta.  Replaces NativeBatchNormBackward0 + ReluBackward0. */
+typedef struct {
+  const float* y; /* raw conv output [M, ld] */
+  float* dA;      /* same layout, overwritten with dY */
+  int ld, coff, C;
+  long M;
+  const float* scale; /* [C] gamma*rstd (as written by finalize) */
+  const float* shift;
+  const float* mean;
+  const float* rstd;
+  int relu;
+  double* sums;   /* workspace [2*C] */
+  float* dgamma;  /* [C] or NULL */
+  float* dbeta;
+} coclr_bn_bwd_t;
+int coclr_bn_bwd(const coclr_bn_bwd_t* p, int num_sms, coclr_stream_t stream);
+
+/* bias+ReLU backward of the projection head (model/pretrain.py:52-53) */
+int coclr_bias_relu_bwd(const float* h, const float* bias, float* dA, float* dbias, int M, int C,
+                        coclr_stream_t stream);
+
+/* ---- nn.MaxPool3d (backbone/s3dg.py:105,151,162,173,190) ---------------------------------------- */
+typedef struct {
+  const float* x; /* input [B,Ti,Hi,Wi,ldx] */
+  int ldx, x_coff;
+  const float* scale; /* pending affine of the input (NULL: none) */
+  const float* shift;
+  int relu;
+  float* y; /* output [B,To,Ho,Wo,ldy] (final values) */
+  int ldy, y_coff;
+  unsigned char* idx; /* [B*To*Ho*Wo, C] arg-max tap */
+  int B, C, Ti, Hi, Wi, To, Ho, Wo;
+  coclr_geom_t g;
+  /* backward only */
+  const float* dy;
+  float* dx;
+  int accumulate;
+} coclr_pool_t;
+int coclr_maxpool_fwd(const coclr_pool_t* p, coclr_stream_t stream);
+int coclr_maxpool_bwd(const coclr_pool_t* p, coclr_stream_t stream);
+
+/* ---- nn.AdaptiveAvgPool3d((1,1,1)) (model/pretrain.py:51) ---------------------------------------- */
+int coclr_avgpool_fwd(const float* x, int ld, int coff, const float* scale, const float* shift, int relu,
+                      float* out, int B, int Pn, int C, coclr_stream_t stream);
+int coclr_avgpool_bwd(const float* dfeat, float* dA, int ld, int coff, int B, int Pn, int C, coclr_stream_t stream);
+
+/* ---- block[:, i].contiguous() + NCDHW->NDHW4 (model/pretrain.py:149-150); batch_index (device int64[B],
+ * or NULL) gathers source clips out[b] = x[batch_index[b]] = the shuffle-BN pick x_gather[idx_this]
+ * (pretrain.py:124) without a separate copy ------------------------------------------------------- */
+int coclr_pack_input(const float* x, long batch_stride, long chan_stride, int Cin, float* out, int B, long thw,
+                     const long* batch_index, coclr_stream_t stream);
+
+/* ---- F.normalize(z + bias, dim=1) (model/pretrain.py:154,167) ------------------------------------- */
+int coclr_l2norm_fwd(const float* z, const float* bias, float* q, float* inv_norm, int B, int D, coclr_stream_t stream);
+int coclr_l2norm_bwd(const float* q, const float* dq, const float* inv_norm, float* dz, float* dbias, int B, int D,
+                     coclr_stream_t stream);
+
+/* ---- _momentum_update_key_encoder (model/pretrain.py:76-80), one launch over the flat parameters -- */
+int coclr_ema_update(float* k, const float* q, float m, float one_minus_m, long n, int num_sms, coclr_stream_t stream);
+
+/* ---- _dequeue_and_enqueue column write (model/pretrain.py:93): queue[:, ptr:ptr+n] = keys^T -------- */
+int coclr_queue_enqueue(float* queue, const float* keys, int dim, int K, int ptr, int n, coclr_stream_t stream);
+
+/* ---- torch.optim.Adam, coupled L2 (main_nce.py:190-200), flat buffers ----------------------------- */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  long n;
+  float grad_scale; /* e.g. 1/world_size after a sum all-reduce */
+  float beta1, beta2, eps, weight_decay;
+  float step_size; /* lr / (1 - beta1^t) */
+  float bc2_sqrt;  /* sqrt(1 - beta2^t) */
+} coclr_adam_t;
+int coclr_adam_step(const coclr_adam_t* p, int num_sms, coclr_stream_t stream);
+
+/* ---- InfoNCE logits + temperature + cross-entropy (model/pretrain.py:175-182; main_nce.py:201,314) ----
+ * logits[b, 0] = q_b.k_b / T, logits[b, 1+j] = q_b.queue[:, j] / T; loss_rows[b] = logsumexp - logits[b,0];
+ * dlogits = d(mean_b loss_rows)/d(logits).  loss_rows / dlogits may be NULL. */
+int coclr_nce_logits_ce(const float* q, const float* k, const float* queue, float T, int B, int D, int K,
+                        float* logits, float* loss_rows, float* dlogits, coclr_stream_t stream);
+/* dq = d(logits)^T contraction with [k | queue] / T (no gradient to k or the queue, pretrain.py:160,176) */
+int coclr_nce_logits_bwd(const float* dlogits, const float* k, const float* queue, float T, int B, int D, int K,
+                         float* dq, coclr_stream_t stream);
 
 #ifdef __cplusplus
 }

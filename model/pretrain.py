@@ -1,0 +1,194 @@
+"""InfoNCE / UberNCE / CoCLR -- drop-in module surface of the reference's model/pretrain.py.
+
+Same constructors, forward signatures, return values, buffers (`queue`, `queue_ptr`, `queue_label`,
+`queue_second`, `queue_vname`) and state_dict key names as TengdaHan/CoCLR model/pretrain.py:28-418, so
+main_nce.py / main_coclr.py and reference checkpoints keep working; the arithmetic runs on coclr_b200's
+sm_100a kernels (CUDA only -- constructing on CPU is fine, calling forward on CPU raises).
+
+What changed under the surface:
+  * encoders run as fused engine passes (coclr_b200.engine), BN/ReLU folded into the convs;
+  * the momentum update is one launch over a flat buffer (reference: 705 launches, pretrain.py:76-80);
+  * shuffle-BN keeps the reference's permutation semantics (rank 0 draws torch.randperm on the CPU RNG and
+    broadcasts, :112-115) but the local pick x_gather[idx_this] is folded into the clip-packing kernel, and
+    the un-shuffle all-gather (:133-143) and the enqueue all-gather (:85) are ONE all-gather;
+  * logits + temperature + cross-entropy by-products come from one kernel (:175-182);
+  * queue_ptr is mirrored on the host, so there is no `int(self.queue_ptr)` device sync per step (:89).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.distributed as dist
+
+from backbone.select_backbone import select_backbone
+from coclr_b200 import moco
+from coclr_b200.moco import concat_all_gather  # noqa: F401  (re-exported: reference defines it here)
+
+
+class InfoNCE(nn.Module):
+    """MoCo for video (reference model/pretrain.py:28-190)."""
+
+    def __init__(self, network='s3d', dim=128, K=2048, m=0.999, T=0.07, precision="parity"):
+        super().__init__()
+        self.dim, self.K, self.m, self.T = dim, K, m, T
+        self.precision = precision
+
+        backbone, self.param = select_backbone(network)
+        feature_size = self.param['feature_size']
+        backbone.precision = precision
+        self.encoder_q = moco.MoCoEncoder(backbone, feature_size, dim, precision)
+        backbone, _ = select_backbone(network)
+        backbone.precision = precision
+        self.encoder_k = moco.MoCoEncoder(backbone, feature_size, dim, precision)
+        for param_q, param_k in zip(self.encoder_q.parameters(), self.encoder_k.parameters()):
+            param_k.data.copy_(param_q.data)      # initialise (pretrain.py:64-66)
+            param_k.requires_grad = False         # not updated by gradient
+
+        self.register_buffer("queue", nn.functional.normalize(torch.randn(dim, K), dim=0))
+        self.register_buffer("queue_ptr", torch.zeros(1, dtype=torch.long))
+        self._ptr_host = None
+
+    # -- queue pointer mirror ---------------------------------------------------------------------
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._ptr_host = None  # re-read the loaded pointer lazily
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _ptr(self):
+        if self._ptr_host is None:
+            self._ptr_host = int(self.queue_ptr)   # one sync after construction / load, not per step
+        return self._ptr_host
+
+    def _advance_ptr(self, n):
+        self._ptr_host = (self._ptr() + n) % self.K
+        self.queue_ptr.fill_(self._ptr_host)
+
+    # -- pieces of the step --------------------------------------------------------------------------
+    @torch.no_grad()
+    def _momentum_update_key_encoder(self):
+        moco.momentum_update(self.encoder_q, self.encoder_k, self.m)
+
+    @torch.no_grad()
+    def _shuffled_keys(self, x2, encoder=None):
+        """shuffle-BN (pretrain.py:98-143): returns (k_local [B, dim], k_global [B*W, dim]) in the ORIGINAL
+        (un-shuffled) order; k_global is what _dequeue_and_enqueue's all-gather (:85) would produce."""
+        encoder = self.encoder_k if encoder is None else encoder
+        world, rank = moco._world()
+        B = x2.shape[0]
+        x_gather = concat_all_gather(x2) if world > 1 else x2
+        idx_shuffle = torch.randperm(B * world).to(x2.device, non_blocking=True)     # CPU RNG draw, as :112
+        if world > 1:
+            dist.broadcast(idx_shuffle, src=0)                                       # :115
+        idx_unshuffle = torch.argsort(idx_shuffle)
+        idx_this = idx_shuffle.view(world, -1)[rank].contiguous()
+        k_sh = encoder.encode(x_gather, batch_index=idx_this, batch=B)            # x_gather[idx_this], :124
+        k_all = concat_all_gather(k_sh) if world > 1 else k_sh
+        k_global = k_all[idx_unshuffle].contiguous()                                  # :143 for every rank
+        return k_global[rank * B:(rank + 1) * B], k_global
+
+    @torch.no_grad()
+    def _dequeue_and_enqueue(self, keys_global):
+        n = keys_global.shape[0]
+        assert self.K % n == 0                                                        # pretrain.py:90
+        ptr = self._ptr()
+        moco.enqueue(self.queue, keys_global, ptr)
+        self._advance_ptr(n)
+        return ptr
+
+    def _qk(self, block):
+        (B, N, *_) = block.shape
+        assert N == 2                                                                 # pretrain.py:148
+        x1, x2 = block[:, 0], block[:, 1]          # views; the .contiguous() copies are folded into packing
+        q = self.encoder_q.encode(x1)
+        in_train_mode = q.requires_grad                                               # :157
+        with torch.no_grad():
+            if in_train_mode:
+                self._momentum_update_key_encoder()                                   # :161
+            k, k_global = self._shuffled_keys(x2)
+        return q, k, k_global, in_train_mode
+
+    def forward(self, block):
+        """block [B,2,C,T,H,W] -> (logits [B,1+K] already / T, labels [B] zeros) (pretrain.py:145-190)."""
+        q, k, k_global, in_train_mode = self._qk(block)
+        logits = moco.nce_logits(q, k, self.queue, self.T)                            # :175-182
+        labels = torch.zeros(logits.shape[0], dtype=torch.long, device=logits.device)  # :185
+        if in_train_mode:
+            self._dequeue_and_enqueue(k_global)                                       # :188
+        return logits, labels
+
+
+class UberNCE(InfoNCE):
+    """Supervised InfoNCE: labels define the positives (reference model/pretrain.py:193-278)."""
+
+    def __init__(self, network='s3d', dim=128, K=2048, m=0.999, T=0.07, precision="parity"):
+        super().__init__(network, dim, K, m, T, precision)
+        self.register_buffer("queue_label", torch.ones(K, dtype=torch.long) * -1)
+
+    def forward(self, block, k_label):
+        q, k, k_global, in_train_mode = self._qk(block)
+        logits = moco.nce_logits(q, k, self.queue, self.T)
+        mask = k_label.unsqueeze(1) == self.queue_label.unsqueeze(0)                  # :271
+        mask = torch.cat([torch.ones((mask.shape[0], 1), dtype=torch.bool, device=mask.device), mask], dim=1)
+        if in_train_mode:
+            with torch.no_grad():
+                labels_global = concat_all_gather(k_label)                            # :215
+                ptr = self._dequeue_and_enqueue(k_global)
+                self.queue_label[ptr:ptr + labels_global.shape[0]] = labels_global    # :224
+        return logits, mask
+
+
+class CoCLR(InfoNCE):
+    """Co-training with a frozen second-view sampler (reference model/pretrain.py:281-418)."""
+
+    def __init__(self, network='s3d', dim=128, K=2048, m=0.999, T=0.07, topk=5, reverse=False, precision="parity"):
+        super().__init__(network, dim, K, m, T, precision)
+        self.topk = topk
+        backbone, _ = select_backbone(network)
+        backbone.precision = precision
+        self.sampler = moco.MoCoEncoder(backbone, self.param['feature_size'], dim, precision)
+        for param_s in self.sampler.parameters():
+            param_s.requires_grad = False
+        self.register_buffer("queue_second", nn.functional.normalize(torch.randn(dim, K), dim=0))
+        self.register_buffer("queue_vname", torch.ones(K, dtype=torch.long) * -1)
+        self.register_buffer("queue_label", torch.ones(K, dtype=torch.long) * -1)
+        self.queue_is_full = False
+        self.reverse = reverse
+
+    def forward(self, block1, block2, k_vsource):
+        (B, N, *_) = block1.shape
+        assert N == 2
+        x1, f1 = block1[:, 0], block1[:, 1]
+        x2, f2 = block2[:, 0], block2[:, 1]
+        if self.reverse:                                                              # :353-355
+            x1, f1 = f1, x1
+            x2, f2 = f2, x2
+        q = self.encoder_q.encode(x1)
+        in_train_mode = q.requires_grad
+        with torch.no_grad():
+            if in_train_mode:
+                self._momentum_update_key_encoder()
+            k, k_global = self._shuffled_keys(x2)
+            kf = self.sampler.encode(f2)                                              # :372-374 (no shuffle)
+        logits = moco.nce_logits(q, k, self.queue, self.T)
+        mask_source = k_vsource.unsqueeze(1) == self.queue_vname.unsqueeze(0)         # :392
+        mask = mask_source.clone()
+        if not self.queue_is_full:
+            self.queue_is_full = bool(torch.all(self.queue_label != -1))              # :400-402
+            if self.queue_is_full:
+                print('\n===== queue is full now =====')
+        if self.queue_is_full and (self.topk != 0):                                   # :404-410
+            mask_sim = kf.matmul(self.queue_second.clone().detach())
+            mask_sim[mask_source] = - np.inf
+            _, topkidx = torch.topk(mask_sim, self.topk, dim=1)
+            topk_onehot = torch.zeros_like(mask_sim)
+            topk_onehot.scatter_(1, topkidx, 1)
+            mask[topk_onehot.bool()] = True
+        mask = torch.cat([torch.ones((mask.shape[0], 1), dtype=torch.bool, device=mask.device), mask], dim=1)
+        if in_train_mode:
+            with torch.no_grad():
+                kf_global = concat_all_gather(kf)
+                vn_global = concat_all_gather(k_vsource)
+                ptr = self._dequeue_and_enqueue(k_global)
+                n = k_global.shape[0]
+                moco.enqueue(self.queue_second, kf_global.contiguous(), ptr)          # :334
+                self.queue_vname[ptr:ptr + n] = vn_global                             # :335
+                self.queue_label[ptr:ptr + n] = torch.ones_like(vn_global)            # :336
+        return logits, mask.detach()

@@ -29,10 +29,28 @@ GRAD_KEYS = ["encoder_q.0.Conv_1a.conv1.weight", "encoder_q.0.Conv_1a.bn2.weight
              "encoder_q.2.weight", "encoder_q.4.bias"]
 
 
+def import_reference():
+    """Import the UNMODIFIED reference's model.pretrain without clashing with this repo's own `model` /
+    `backbone` packages (same top-level names by design: they are drop-ins)."""
+    import importlib
+    clash = lambda k: k in ("model", "backbone") or k.startswith("model.") or k.startswith("backbone.")
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if clash(k)}
+    sys.path.insert(0, REF)
+    try:
+        mod = importlib.import_module("model.pretrain")
+        assert mod.__file__.startswith(REF), mod.__file__
+    finally:
+        sys.path.remove(REF)
+        for k in list(sys.modules):
+            if clash(k):
+                sys.modules.pop(k)
+        sys.modules.update(saved)
+    return mod
+
+
 def run_reference(K=128, B=4, T=8, ptr=16, threads=8):
     import torch.distributed as dist
-    sys.path.insert(0, REF)
-    from model.pretrain import InfoNCE  # the unmodified reference
+    InfoNCE = import_reference().InfoNCE  # the unmodified reference
     from oracle import coclr_oracle as O
     torch.set_num_threads(threads)
     torch.Tensor.cuda = lambda self, *a, **k: self  # pretrain.py:112,185 hard-code .cuda(); CPU shim

@@ -1,0 +1,100 @@
+"""CPU-side checks: C-ABI library builds/loads/exports every declared symbol, the nn.Module surface has
+the reference's state_dict keys, the engine graph covers exactly the reference's parameters, and the product
+refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_all_header_symbols():
+    from coclr_b200 import build, lib, _signatures
+    path = build.build()
+    assert os.path.exists(path)
+    cdll = lib.load()
+    header = open(os.path.join(ROOT, "include", "coclr_b200.h")).read()
+    declared = set(re.findall(r"\b(coclr_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(cdll, name), "library does not export %s" % name
+    assert declared == set(_signatures.EXPORTS), declared ^ set(_signatures.EXPORTS)
+
+
+def test_library_is_sm100a_tcgen05():
+    import subprocess
+    from coclr_b200 import build
+    sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "UTCHMMA" in sass and "LDTM" in sass and "UBLKCP" in sass
+
+
+def test_state_dict_keys_match_reference_surface():
+    from model.pretrain import InfoNCE, UberNCE, CoCLR
+    from oracle import coclr_oracle as O
+    m = InfoNCE("s3d", 128, 128)
+    want = set(O.with_aliases(O.synth_state(O.infonce_shapes(128, 128))).keys())
+    have = set(m.state_dict().keys())
+    assert want == have, (sorted(want - have)[:5], sorted(have - want)[:5])
+    assert len(list(m.encoder_q.parameters())) == 235
+    assert not any(p.requires_grad for p in m.encoder_k.parameters())
+    u = UberNCE("s3d", 128, 128)
+    assert "queue_label" in u.state_dict()
+    c = CoCLR("s3d", 128, 128, topk=5)
+    for k in ("queue_second", "queue_vname", "queue_label", "sampler.0.Conv_1a.conv1.weight", "sampler.4.bias"):
+        assert k in c.state_dict(), k
+    assert c.queue_is_full is False
+    if os.path.isdir("/root/reference/model"):
+        sys.path.insert(0, "/root/reference")
+        import importlib
+        ref = importlib.import_module("model.pretrain") if False else None  # name clash with our package: compare via oracle aliases instead
+
+
+def test_select_backbone_contract():
+    from backbone.select_backbone import select_backbone
+    m, p = select_backbone("s3d")
+    assert p == {"feature_size": 1024}
+    with pytest.raises(NotImplementedError):
+        select_backbone("nope")
+
+
+def test_graph_covers_reference_parameters():
+    from coclr_b200.engine import Graph
+    from coclr_b200.s3d_spec import s3d_stages
+    from oracle import coclr_oracle as O
+    g = Graph(s3d_stages(3), 3, head_dim=128, bb_prefix="0.")
+    lay = dict(g.param_layout())
+    shapes = {k[len("encoder_q."):]: tuple(v) for k, v in O.infonce_shapes(128, 128).items()
+              if k.startswith("encoder_q.") and (k.endswith(".weight") or k.endswith(".bias"))}
+    assert set(lay) == set(shapes)
+    for k, s in shapes.items():
+        assert tuple(lay[k]) == s, k
+    bufs = dict(g.buffer_layout())
+    rm = {k[len("encoder_q."):-len(".running_mean")]: v[0] for k, v in O.infonce_shapes(128, 128).items()
+          if k.startswith("encoder_q.") and k.endswith(".running_mean")}
+    assert bufs == rm
+    # 77 backbone convs, 13 pools
+    assert sum(1 for k, _ in g.items if k == "conv") == 77
+    assert sum(1 for k, _ in g.items if k == "pool") == 13
+    # shapes at 32 x 128^2
+    dims = g.backbone_out.dims_fn((32, 128, 128))
+    assert dims == (4, 4, 4) and g.backbone_out.C == 1024
+
+
+def test_no_cpu_fallback():
+    from model.pretrain import InfoNCE
+    m = InfoNCE("s3d", 128, 128)
+    with pytest.raises(Exception) as ei:
+        m(torch.zeros(2, 2, 3, 8, 64, 64))
+    assert "CUDA" in str(ei.value)
+
+
+def test_oracle_not_imported_by_product():
+    import subprocess
+    out = subprocess.run(["grep", "-rIl", "-E", r"^\s*(from|import) +oracle", os.path.join(ROOT, "coclr_b200"),
+                          os.path.join(ROOT, "model"), os.path.join(ROOT, "backbone")], capture_output=True, text=True)
+    assert out.stdout.strip() == ""
