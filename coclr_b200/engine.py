@@ -396,10 +396,12 @@ class Plan:
                 convs_into.setdefault(it.dst.index, []).append(it)
             elif kind == "pool":
                 pool_into[it.dst.index] = it
-        for t in reversed(g.tensors):
-            a = acts[t.index]
-            if t is g.input:
+        # reverse forward order: a tensor is handled at its BatchNorm / pool item, i.e. after every consumer
+        for kind_r, it_r in reversed(g.items):
+            if kind_r == "conv":
                 continue
+            t = it_r if kind_r == "bn" else it_r.dst
+            a = acts[t.index]
             if not a.grad_written:
                 raise RuntimeError("tensor %s never receives a gradient" % t.name)
             if t.pending:

@@ -114,10 +114,13 @@ def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+DRY_RUN = False  # tests only: lets launch plans be BUILT (never run) over CPU tensors to validate their structure
+
+
 def dptr(t):
     if t is None:
         return None
-    if not t.is_cuda:
+    if not t.is_cuda and not DRY_RUN:
         raise CoclrError("coclr_b200 ops need CUDA tensors (no CPU fallback)")
     return C.c_void_p(t.data_ptr())
 
@@ -126,6 +129,8 @@ _num_sms = {}
 
 
 def num_sms(device=None):
+    if DRY_RUN:
+        return 148
     dev = torch.cuda.current_device() if device is None else torch.device(device).index
     if dev not in _num_sms:
         _num_sms[dev] = torch.cuda.get_device_properties(dev).multi_processor_count

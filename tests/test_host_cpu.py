@@ -98,3 +98,33 @@ def test_oracle_not_imported_by_product():
     out = subprocess.run(["grep", "-rIl", "-E", r"^\s*(from|import) +oracle", os.path.join(ROOT, "coclr_b200"),
                           os.path.join(ROOT, "model"), os.path.join(ROOT, "backbone")], capture_output=True, text=True)
     assert out.stdout.strip() == ""
+
+
+def test_launch_plans_build_on_cpu_dry_run():
+    """Structure of the forward/backward launch lists (built over CPU tensors, never run): every tensor gets
+    a gradient, op counts match the architecture, first-writer/accumulate flags are consistent."""
+    from coclr_b200 import lib as L
+    from coclr_b200.engine import Graph, ParamStore, EncoderEngine
+    from coclr_b200.s3d_spec import s3d_stages
+    L.DRY_RUN = True
+    try:
+        g = Graph(s3d_stages(3), 3, head_dim=128, bb_prefix="0.")
+        st = ParamStore(g, torch.device("cpu"))
+        eng = EncoderEngine(st, g, "parity")
+        p = eng.plan(2, 8, 64, 64, True, True)
+        names = [fn.__name__ for fn, _ in p.fwd]
+        assert names.count("coclr_conv_igemm") == 77 + 2
+        assert names.count("coclr_maxpool_fwd") == 13
+        assert names.count("coclr_bn_finalize") == 77 - 9 * 3   # one finalize per tensor; concat tensors hold 4 BNs
+        bn = [fn.__name__ for fn, _ in p.bwd]
+        assert bn.count("coclr_conv_wgrad") == 77 + 2
+        assert bn.count("coclr_conv_igemm") == 76 + 2           # no dgrad for the RGB stem conv
+        assert bn.count("coclr_maxpool_bwd") == 13
+        assert bn.count("coclr_bn_bwd") == names.count("coclr_bn_finalize")
+        # inference plan has no gradient buffers
+        p2 = eng.plan(2, 8, 64, 64, True, False)
+        assert not p2.bwd and all(a.grad is None for a in p2.acts.values())
+        # flat layout: every BN group contiguous, every offset 16-byte aligned
+        assert all(off % 4 == 0 for off, _, _ in st.offsets.values())
+    finally:
+        L.DRY_RUN = False
