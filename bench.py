@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the CoCLR hot path (BASELINE.json metric: clips/sec, S3D InfoNCE, 32 x 128^2 clips, K=2048).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+A "step" is one full training step on a per-GPU batch of 32 clip pairs: q-encoder forward, EMA, shuffle-BN key
+forward, fused logits+CE, enqueue, full backward, gradient all-reduce, Adam.  clips/sec = 2*B*W / step time.
+`value` times steps whose inputs are already resident in HBM; `e2e` times the same public-API call fed from pinned
+host memory (H2D of every step's 403 MB block inside the timed region, prefetched on a copy stream, plus a D2H read
+of the loss every step).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(network="s3d", dim=128, K=2048, m=0.999, T=0.07, B=32, seq_len=32, img=128)
+GFLOP_PER_PAIR = 91.46  # q fwd+dgrad+wgrad, k fwd (conv MACs x2), one clip pair
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="coclr_b200", choices=["coclr_b200", "reference"])
+    ap.add_argument("--precision", default="parity", choices=["parity", "mixed", "fast"])
+    ap.add_argument("--batch", type=int, default=CFG["B"])
+    ap.add_argument("--seq_len", type=int, default=CFG["seq_len"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print the per-kernel time table of one step to stderr")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm restated in oracle/ (the Python reference itself cannot travel to the GPU box)
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_clips_per_s(batch, seq_len, img, K, steps, warmup):
+    from oracle import coclr_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    sd = O.synth_state(O.infonce_shapes(128, K), seed=0)
+    for k in O.param_keys(sd, "encoder_q."):
+        sd[k].requires_grad_(True)
+    state = {}
+    g = torch.Generator().manual_seed(1)
+    times = []
+    for it in range(warmup + steps):
+        block = torch.randn(batch, 2, 3, seq_len, img, img, generator=g)
+        t0 = time.perf_counter()
+        idx = torch.randperm(batch)
+        logits, labels = O.infonce_forward(sd, [block], idx)
+        loss = O.infonce_loss(logits[0], labels)
+        qkeys = O.param_keys(sd, "encoder_q.")
+        grads = torch.autograd.grad(loss, [sd[k] for k in qkeys])
+        O.adam_step({k: sd[k] for k in qkeys}, dict(zip(qkeys, grads)), state)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return 2.0 * batch / med, med
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 2
+    steps = max(1, min(args.steps, 3))
+    val, med = cpu_oracle_clips_per_s(batch, args.seq_len, CFG["img"], CFG["K"], steps, 1)
+    line = {"impl": "reference", "metric": "clips/sec S3D InfoNCE (32x128^2, K=2048)", "value": val, "unit": "clips/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": med * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "InfoNCE S3D K=2048 seq_len=%d 128^2 full train step (fwd+bwd+Adam)" % args.seq_len,
+                       "batch_per_step": batch},
+            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "oracle port of the reference (torch CPU fp32), %d timed steps of batch %d "
+                                       "clip pairs after 1 warm-up; reference is pure Python and cannot travel"
+                                       % (steps, batch)},
+            "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# roofline of the dominant kernel (coclr_conv_igemm) from per-launch CUDA events of one step
+# ------------------------------------------------------------------------------------------------
+def conv_flops(cv):
+    """Algorithmic FLOPs of one coclr_conv_igemm launch (2 x MACs of the convolution it implements)."""
+    if cv.g.transposed:   # dgrad: one MAC per (dy pixel, tap, cin, cout) of the forward conv
+        pix = cv.B * cv.src.T * cv.src.H * cv.src.W
+        return 2.0 * pix * cv.N * cv.g.kt * cv.g.kh * cv.g.kw * cv.src.C
+    pix = cv.B * cv.Td * cv.Hd * cv.Wd
+    cin = 3 if cv.src.C == 4 else cv.src.C   # RGB stem is stored with a zero 4th channel
+    return 2.0 * pix * cv.N * cv.g.kt * cv.g.kh * cv.g.kw * cin
+
+
+def wgrad_flops(wg):
+    pix = wg.B * wg.Td * wg.Hd * wg.Wd
+    return 2.0 * pix * wg.Cout * wg.g.kt * wg.g.kh * wg.g.kw * wg.Cin_real
+
+
+def kernel_breakdown(run_step):
+    from coclr_b200.engine import EncoderEngine
+    EncoderEngine.profile = []
+    try:
+        run_step()
+        torch.cuda.synchronize()
+        prof = EncoderEngine.profile
+    finally:
+        EncoderEngine.profile = None
+    table = {}
+    for name, a, e0, e1 in prof:
+        ms = e0.elapsed_time(e1)
+        t = table.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0})
+        t["launches"] += 1
+        t["ms"] += ms
+        if name == "coclr_conv_igemm":
+            t["flops"] += conv_flops(a[0]._obj)
+        elif name == "coclr_conv_wgrad":
+            t["flops"] += wgrad_flops(a[0]._obj)
+    return table, prof
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from model.pretrain import InfoNCE
+    from coclr_b200 import moco, lib as L
+
+    B, T, HW, K = args.batch, args.seq_len, CFG["img"], CFG["K"]
+    torch.manual_seed(0)                                   # main_nce.py:97-99
+    model = InfoNCE(CFG["network"], CFG["dim"], K, CFG["m"], CFG["T"], precision=args.precision).to(dev).train()
+    opt = moco.FlatAdam(model.encoder_q, lr=1e-3, weight_decay=1e-5)
+    gen = torch.Generator().manual_seed(1000 + rank)
+    host_blocks = [torch.randn(B, 2, 3, T, HW, HW, generator=gen).pin_memory() for _ in range(2)]
+    dev_blocks = [hb.to(dev) for hb in host_blocks]       # 2 x 403 MB > 126 MB L2: inputs never L2-resident
+    loss_keep = [None]
+
+    def train_step(block):
+        logits, labels = model(block)
+        loss = moco.nce_cross_entropy(logits, labels)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        loss_keep[0] = loss
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident inputs ----
+    for i in range(args.warmup):
+        train_step(dev_blocks[i % 2])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = L.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        train_step(dev_blocks[i % 2])
+    e1.record()
+    barrier()
+    launches = (L.LAUNCHES - l0) // max(1, args.steps)
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    final_loss = float(loss_keep[0])
+    value = 2.0 * B * world / (ms * 1e-3)
+
+    # ---- end to end: pinned host inputs, H2D inside the timed region (prefetched), loss read back every step ----
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream()
+        stage = [torch.empty_like(dev_blocks[0]) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[i % 2])          # the step that last used this buffer has finished
+                stage[i % 2].copy_(host_blocks[i % 2], non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def e2e_loop(n):
+            for d in done:
+                d.record()
+            prefetch(0)
+            for i in range(n):
+                if i + 1 < n:
+                    prefetch(i + 1)
+                torch.cuda.current_stream().wait_event(ready[i % 2])
+                loss = train_step(stage[i % 2])
+                done[i % 2].record()
+                loss.item()                                  # D2H read of the step's result
+        e2e_loop(max(1, args.warmup // 2))
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(args.steps)
+        barrier()
+        dt = (time.perf_counter() - t0) / args.steps
+        tt = torch.tensor([dt], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": 2.0 * B * world / float(tt), "unit": "clips/s",
+               "h2d_bytes_per_step": host_blocks[0].numel() * 4, "d2h_bytes_per_step": 4}
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- roofline of the dominant kernel, measured live with CUDA events around every launch of one step ----
+    table, prof = kernel_breakdown(lambda: train_step(dev_blocks[0]))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    cv = table.get("coclr_conv_igemm", {"ms": 0.0, "flops": 0.0, "launches": 0})
+    wg = table.get("coclr_conv_wgrad", {"ms": 0.0, "flops": 0.0, "launches": 0})
+    passes = 3 if args.precision == "parity" else None
+    achieved = cv["flops"] / (cv["ms"] * 1e-3) / 1e12 if cv["ms"] > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "coclr_conv_igemm (forward + dgrad implicit GEMM)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "traffic": None, "peak_source": peak_src,
+                "launches_per_step": cv["launches"], "ms_per_step_in_kernel": cv["ms"],
+                "mode": "%s (forward %s, backward %s)" % (args.precision,
+                                                        "3 MMA passes fp16 hi/lo" if args.precision != "fast" else "1 pass bf16",
+                                                        "3 MMA passes bf16 hi/lo" if args.precision == "parity" else "1 pass bf16"),
+                "tensor_work_frac": (achieved * 3 / peak_tf) if passes else None,
+                "wgrad": {"achieved": wg["flops"] / (wg["ms"] * 1e-3) / 1e12 if wg["ms"] > 0 else 0.0,
+                          "ms_per_step_in_kernel": wg["ms"], "launches_per_step": wg["launches"]},
+                "step_breakdown_ms": {k: round(v["ms"], 3) for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])}}
+    if args.breakdown and rank == 0:
+        for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"]):
+            print("%-24s %5d launches %9.3f ms" % (k, v["launches"], v["ms"]), file=sys.stderr)
+        rows = []
+        for name, a, s0, s1 in prof:
+            if name in ("coclr_conv_igemm", "coclr_conv_wgrad"):
+                o = a[0]._obj
+                fl = conv_flops(o) if name == "coclr_conv_igemm" else wgrad_flops(o)
+                msl = s0.elapsed_time(s1)
+                if name == "coclr_conv_igemm":
+                    desc = "M=%d N=%d K=%d tr=%d" % (o.B * o.Td * o.Hd * o.Wd, o.N, o.Kreal, o.g.transposed)
+                else:
+                    desc = "M=%d Cout=%d K=%d splits=%d" % (o.B * o.Td * o.Hd * o.Wd, o.Cout,
+                                                           o.g.kt * o.g.kh * o.g.kw * o.src.C, o.splits)
+                rows.append((msl, name, desc, fl / (msl * 1e-3) / 1e12))
+        rows.sort(reverse=True)
+        for msl, name, desc, tf in rows[:40]:
+            print("%8.3f ms %-18s %-40s %7.1f TF/s" % (msl, name[6:], desc, tf), file=sys.stderr)
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                v, med = cpu_oracle_clips_per_s(2, T, HW, K, 2, 1)
+                cpu = {"value": v, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+                       "sample": "oracle port (torch CPU fp32) full train step, batch 2 clip pairs, 2 timed steps after 1 warm-up"}
+            except Exception as ex:  # pragma: no cover
+                cpu = {"value": None, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+                       "sample": "failed: %r" % (ex,)}
+        line = {"metric": "clips/sec S3D InfoNCE (32x128^2, K=2048)", "value": value, "unit": "clips/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (fp16/bf16 hi-lo split operands, fp32 accumulate)" if args.precision == "parity" else
+                         ("bf16" if args.precision == "fast" else "f32 forward / bf16 backward"),
+                "data": "synthetic",
+                "config": {"workload": "InfoNCE S3D moco-k=2048 bs=%d/GPU seq_len=%d 128^2, full train step "
+                                       "(q fwd, EMA, shuffle-BN k fwd, fused logits+CE, enqueue, bwd, all-reduce, Adam)"
+                                       % (B, T),
+                           "global_batch": B * world, "parallelism": "dp%d" % world, "precision": args.precision,
+                           "l2": "two alternating 403 MB input blocks per rank (> 126 MB L2)",
+                           "pairs_per_s": value / 2, "final_loss": final_loss,
+                           "algorithmic_tflops": value / 2 * GFLOP_PER_PAIR / 1e3},
+                "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

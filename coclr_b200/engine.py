@@ -496,13 +496,22 @@ class EncoderEngine:
             self.plans[key] = p
         return p
 
-    @staticmethod
-    def _run(oplist):
+    profile = None  # set to a list to collect (fn name, start event, end event) per launch (bench / tuning only)
+
+    def _run(self, oplist):
         stream = L.stream_ptr()
+        prof = EncoderEngine.profile
         for fn, args in oplist:
+            if prof is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             rc = fn(*args, stream)
+            if prof is not None:
+                e1.record()
+                prof.append((fn.__name__, args, e0, e1))
             if rc != 0:
                 raise L.CoclrError("%s failed with code %d" % (fn.__name__, rc))
+        L.LAUNCHES += sum(L.KERNELS_PER_CALL.get(fn.__name__, 1) for fn, _ in oplist)
 
     def forward(self, x, training=True, with_backward=False, repack=True, batch_index=None, batch=None):
         """x: [*, C, T, H, W] fp32 CUDA (any batch stride). Clip b of the pass is x[batch_index[b]] when a

@@ -105,9 +105,15 @@ def load():
     return lib
 
 
+LAUNCHES = 0  # kernels of this library launched so far in this process (bench.py reports the per-step count)
+KERNELS_PER_CALL = {"coclr_bn_bwd": 2, "coclr_l2norm_bwd": 2, "coclr_conv_packed_bytes": 0}
+
+
 def check(rc, what):
+    global LAUNCHES
     if rc != 0:
         raise CoclrError("%s failed with code %d" % (what, rc))
+    LAUNCHES += KERNELS_PER_CALL.get(what, 1)
 
 
 def stream_ptr():
