@@ -13,14 +13,15 @@ EXPORTS = {
     "coclr_conv_packed_bytes": (C.c_size_t, [I, I, C.POINTER(I), C.POINTER(I)]),
     "coclr_conv_wgrad": (I, [P, P]),
     "coclr_pack_weights": (I, [P, P]),
+    "coclr_affine_split": (I, [P, I, P]),
     "coclr_bn_finalize": (I, [P, P]),
     "coclr_bn_bwd": (I, [P, I, P]),
     "coclr_bias_relu_bwd": (I, [P, P, P, P, I, I, P]),
     "coclr_maxpool_fwd": (I, [P, P]),
     "coclr_maxpool_bwd": (I, [P, P]),
-    "coclr_avgpool_fwd": (I, [P, I, I, P, P, I, P, I, I, I, P]),
+    "coclr_avgpool_fwd": (I, [P, P, I, I, P, I, I, I, P]),
     "coclr_avgpool_bwd": (I, [P, P, I, I, I, I, I, P]),
-    "coclr_pack_input": (I, [P, LG, LG, I, P, I, LG, P, P]),
+    "coclr_pack_input": (I, [P, LG, LG, I, P, P, I, LG, P, P]),
     "coclr_l2norm_fwd": (I, [P, P, P, P, I, I, P]),
     "coclr_l2norm_bwd": (I, [P, P, P, P, P, I, I, P]),
     "coclr_ema_update": (I, [P, P, F, F, LG, I, P]),

@@ -77,6 +77,18 @@ COCLR_DEVINL void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
       : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS); src_bytes = 0 zero-fills the destination
+// (convolution padding / ragged edges) without touching global memory.
+COCLR_DEVINL void cp_async16(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes)
+               : "memory");
+}
+COCLR_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+COCLR_DEVINL void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05: tensor memory + MMA
 // ---------------------------------------------------------------------------------------------
@@ -138,13 +150,13 @@ COCLR_DEVINL uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uin
   return d;
 }
 
-// Instruction descriptor for kind::f16: fp32 accumulate, A/B format 0 = fp16, 1 = bf16.
-COCLR_DEVINL uint32_t make_idesc(uint32_t ab_format, uint32_t a_mn_major, uint32_t b_mn_major, uint32_t M,
-                                 uint32_t N) {
+// Instruction descriptor for kind::f16: fp32 accumulate, A / B format 0 = fp16, 1 = bf16 (independent).
+COCLR_DEVINL uint32_t make_idesc(uint32_t a_format, uint32_t b_format, uint32_t a_mn_major, uint32_t b_mn_major,
+                                 uint32_t M, uint32_t N) {
   uint32_t d = 0;
-  d |= 1u << 4;                 // c_format = F32
-  d |= (ab_format & 7u) << 7;   // a_format
-  d |= (ab_format & 7u) << 10;  // b_format
+  d |= 1u << 4;                // c_format = F32
+  d |= (a_format & 7u) << 7;   // a_format
+  d |= (b_format & 7u) << 10;  // b_format
   d |= (a_mn_major & 1u) << 15;
   d |= (b_mn_major & 1u) << 16;
   d |= ((N >> 3) & 0x3Fu) << 17;

@@ -6,17 +6,17 @@
 // dgrad / wgrad that loss.backward() (main_nce.py:330) dispatches.
 //
 // Design:
-//  * activations are channels-last fp32 in HBM, *pre*-BatchNorm; the consumer applies
-//    relu(scale*x+shift) while it gathers its operand tile (BN-apply + ReLU never touch HBM);
-//  * producer warps gather 128 pixels x 64 K-elements, split every value into a 16-bit (hi, lo)
-//    pair and store both into 128B-swizzled shared-memory tiles; weights arrive pre-split and
-//    pre-swizzled through one bulk (TMA-engine) copy per stage;
-//  * one elected thread issues tcgen05.mma (M=128, N<=256, K=16) for the three products
-//    hi*lo, lo*hi, hi*hi into one fp32 TMEM accumulator (fp32-equivalent result), or hi*hi only
-//    in single-pass mode;
-//  * four epilogue warps drain a second TMEM accumulator of the previous tile concurrently,
-//    transpose through shared memory for coalesced stores and accumulate the per-channel
-//    sum / sum-of-squares that train-mode BatchNorm needs.
+//  * every activation a conv consumes lives in HBM as a pair of channels-last 16-bit planes (hi, lo) with
+//    hi + lo == the fp32 value to ~22 bits (fp16 pair) -- written once by the BatchNorm-apply/ReLU/split
+//    kernel (or the pooling kernel) that finalises the producer's output;
+//  * producer warps only generate addresses: 16-byte cp.async (LDGSTS) copies with hardware zero-fill for
+//    padding land 128 pixels x 64 K-elements straight in 128B-swizzled shared-memory tiles; weights arrive
+//    pre-split and pre-swizzled through one bulk (TMA-engine) copy per stage;
+//  * one elected thread issues tcgen05.mma (M=128, N<=256, K=16) for the three products hi*lo, lo*hi, hi*hi
+//    into one fp32 TMEM accumulator (fp32-equivalent result), or hi*hi only in single-pass mode;
+//  * four epilogue warps drain the other TMEM accumulator (previous tile) concurrently, transpose through
+//    shared memory for coalesced stores and accumulate the per-channel sum / sum-of-squares that train-mode
+//    BatchNorm needs.
 #include "common.cuh"
 #include "coclr_b200.h"
 
@@ -29,10 +29,7 @@ static constexpr int kEpiWarps = 4;
 // warp roles: [0,4) epilogue, [4,12) producers, 12 MMA issuer, 13 weight loader + TMEM owner
 static constexpr int kThreads = (kEpiWarps + kProducerWarps + 2) * 32;
 static constexpr int kStagePitch = 33;  // floats per staged row (conflict-free transpose)
-
-struct RowSet8 {
-  int b[8], t[8], y[8], x[8];  // b < 0 : row outside the problem
-};
+static constexpr int kMaxStages = 6;
 
 // Decompose destination pixel m into the source-space base coordinates used by the gather.
 COCLR_DEVINL void row_coords(const coclr_geom_t& G, int Td, int Hd, int Wd, int M, int m, int& b, int& t, int& y,
@@ -59,17 +56,16 @@ COCLR_DEVINL void row_coords(const coclr_geom_t& G, int Td, int Hd, int Wd, int 
   }
 }
 
-// Gather NI*16 rows x 64 K-columns [kbase, kbase+64) of the implicit operand into one swizzled
-// [rows][128 B] block (hi) and its lo twin.  Thread (kg, r0) owns 4 consecutive K elements of rows
-// r0 + 16*i.  K index k = tap*C + channel; C % 4 == 0 so a float4 never straddles taps.
-template <bool kBf16, bool kLo, int NI>
-COCLR_DEVINL void gather_block(const coclr_src_t& S, const coclr_geom_t& G, int Kreal, int kbase, int kg, int r0,
-                               const int* rb, const int* rt, const int* ry, const int* rx, uint8_t* blk_hi,
-                               uint8_t* blk_lo) {
-  const int k0 = kbase + kg * 4;
+// Issue the cp.async copies of NI*32 rows x 64 K-columns [kbase, kbase+64) of the implicit operand into one
+// swizzled [rows][128 B] block (hi plane) and its lo twin.  Thread (ck, r0) owns the 16-byte chunk ck
+// (8 consecutive K elements) of rows r0 + 32*i.  K index k = tap*C + channel, C % 8 == 0.
+template <bool kLo, int NI>
+COCLR_DEVINL void gather_block_async(const coclr_src_t& S, const coclr_geom_t& G, int Kreal, int kbase, int ck, int r0,
+                                     const int* rb, const int* rt, const int* ry, const int* rx, uint32_t blk_hi,
+                                     uint32_t blk_lo) {
+  const int k0 = kbase + ck * 8;
   const bool kvalid = k0 < Kreal;
   int ta = 0, ya = 0, xa = 0, ci = 0;
-  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
   if (kvalid) {
     int tap = k0 / S.C;
     ci = k0 - tap * S.C;
@@ -78,69 +74,33 @@ COCLR_DEVINL void gather_block(const coclr_src_t& S, const coclr_geom_t& G, int 
     int rem = tap - ta * khw;
     ya = rem / G.kw;
     xa = rem - ya * G.kw;
-    if (S.scale != nullptr) {
-      sc = __ldg(reinterpret_cast<const float4*>(S.scale + ci));
-      sh = __ldg(reinterpret_cast<const float4*>(S.shift + ci));
-    }
   }
-  float4 v[NI];
-  bool ok[NI];
+  const uint16_t* hi = reinterpret_cast<const uint16_t*>(S.hi);
+  const uint16_t* lo = reinterpret_cast<const uint16_t*>(S.lo);
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
-    ok[i] = false;
-    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (kvalid && rb[i] >= 0) {
-      int ts, ys, xs;
-      bool in;
-      if (!G.transposed) {
-        ts = rt[i] + ta;
-        ys = ry[i] + ya;
-        xs = rx[i] + xa;
-        in = true;
-      } else {
-        ts = rt[i] - ta;
-        ys = ry[i] - ya;
-        xs = rx[i] - xa;
-        in = (ts >= 0) && (ys >= 0) && (xs >= 0);
-        if (G.st == 2) { in = in && !(ts & 1); ts >>= 1; }
-        if (G.sh == 2) { in = in && !(ys & 1); ys >>= 1; }
-        if (G.sw == 2) { in = in && !(xs & 1); xs >>= 1; }
-      }
-      in = in && ((unsigned)ts < (unsigned)S.T) && ((unsigned)ys < (unsigned)S.H) && ((unsigned)xs < (unsigned)S.W);
-      if (in) {
-        size_t off = ((((size_t)rb[i] * S.T + ts) * S.H + ys) * S.W + xs) * (size_t)S.ld + S.coff + ci;
-        v[i] = ldg_nc_f4(S.ptr + off);
-        ok[i] = true;
-      }
+    bool in = kvalid && rb[i] >= 0;
+    int ts, ys, xs;
+    if (!G.transposed) {
+      ts = rt[i] + ta;
+      ys = ry[i] + ya;
+      xs = rx[i] + xa;
+    } else {
+      ts = rt[i] - ta;
+      ys = ry[i] - ya;
+      xs = rx[i] - xa;
+      in = in && (ts >= 0) && (ys >= 0) && (xs >= 0);
+      if (G.st == 2) { in = in && !(ts & 1); ts >>= 1; }
+      if (G.sh == 2) { in = in && !(ys & 1); ys >>= 1; }
+      if (G.sw == 2) { in = in && !(xs & 1); xs >>= 1; }
     }
-  }
-#pragma unroll
-  for (int i = 0; i < NI; ++i) {
-    float4 a = v[i];
-    if (ok[i]) {
-      a.x = fmaf(a.x, sc.x, sh.x);
-      a.y = fmaf(a.y, sc.y, sh.y);
-      a.z = fmaf(a.z, sc.z, sh.z);
-      a.w = fmaf(a.w, sc.w, sh.w);
-      if (S.relu) {
-        a.x = fmaxf(a.x, 0.f);
-        a.y = fmaxf(a.y, 0.f);
-        a.z = fmaxf(a.z, 0.f);
-        a.w = fmaxf(a.w, 0.f);
-      }
-    }
-    uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
-    split2<kBf16>(a.x, h0, l0);
-    split2<kBf16>(a.y, h1, l1);
-    split2<kBf16>(a.z, h2, l2);
-    split2<kBf16>(a.w, h3, l3);
-    const uint32_t off = swz128_offset((uint32_t)(r0 + 16 * i), (uint32_t)(kg >> 1)) + (uint32_t)(kg & 1) * 8u;
-    *reinterpret_cast<uint2*>(blk_hi + off) =
-        make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
-    if constexpr (kLo) {
-      *reinterpret_cast<uint2*>(blk_lo + off) =
-          make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
-    }
+    in = in && ((unsigned)ts < (unsigned)S.T) && ((unsigned)ys < (unsigned)S.H) && ((unsigned)xs < (unsigned)S.W);
+    size_t off = 0;
+    if (in) off = ((((size_t)rb[i] * S.T + ts) * S.H + ys) * S.W + xs) * (size_t)S.ld + S.coff + ci;
+    const uint32_t dst = swz128_offset((uint32_t)(r0 + 32 * i), (uint32_t)ck);
+    const uint32_t nbytes = in ? 16u : 0u;
+    cp_async16(blk_hi + dst, hi + off, nbytes);
+    if constexpr (kLo) cp_async16(blk_lo + dst, lo + off, nbytes);
   }
 }
 
@@ -167,7 +127,7 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(int BN, int n_tiles, 
   const uint32_t fixed = kEpiWarps * 32u * kStagePitch * 4u + (want_stats ? 2u * n_tiles * BN * 8u : 0u) + 256u;
   const uint32_t budget = 227u * 1024u - 1024u /*alignment slack*/ - fixed;
   uint32_t st = budget / L.stage_bytes;
-  if (st > 6) st = 6;
+  if (st > (uint32_t)kMaxStages) st = kMaxStages;
   L.stages = st;
   L.off_stage = L.stages * L.stage_bytes;
   L.off_stats = L.off_stage + kEpiWarps * 32u * kStagePitch * 4u;
@@ -176,7 +136,7 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(int BN, int n_tiles, 
   return L;
 }
 
-template <bool kBf16, int kNPass>
+template <int kNPass>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_conv_t P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -190,9 +150,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
 
   float* stage_buf = reinterpret_cast<float*>(smem + L.off_stage);
   double* sstats = reinterpret_cast<double*>(smem + L.off_stats);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.off_bars);  // [6]
-  uint64_t* empty_bar = full_bar + 6;                                    // [6]
-  uint64_t* tfull_bar = empty_bar + 6;                                   // [2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.off_bars);  // [kMaxStages]
+  uint64_t* empty_bar = full_bar + kMaxStages;                           // [kMaxStages]
+  uint64_t* tfull_bar = empty_bar + kMaxStages;                          // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                                  // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -200,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (uint32_t s = 0; s < 6; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&full_bar[s], kProducerWarps + 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -222,26 +182,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp >= kEpiWarps && warp < kEpiWarps + kProducerWarps) {
-    // ===================== A-operand producers =====================
+    // ===================== A-operand producers (address generation + cp.async only) =====================
     const int pt = threadIdx.x - kEpiWarps * 32;  // 0..255
-    const int kg = pt & 15;
-    const int r0 = pt >> 4;
+    const int ck = pt & 7;
+    const int r0 = pt >> 3;  // 0..31; rows r0 + 32*i
+    const uint32_t smem_base = smem_u32(smem);
     uint32_t stage = 0, phase = 0;
+    int prev_stage = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / P.n_tiles;
-      int rb[8], rt[8], ry[8], rx[8];
+      int rb[4], rt[4], ry[4], rx[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        row_coords(P.g, P.Td, P.Hd, P.Wd, M, m_tile * kTileM + r0 + 16 * i, rb[i], rt[i], ry[i], rx[i]);
+      for (int i = 0; i < 4; ++i)
+        row_coords(P.g, P.Td, P.Hd, P.Wd, M, m_tile * kTileM + r0 + 32 * i, rb[i], rt[i], ry[i], rx[i]);
       for (int kc = 0; kc < nkc; ++kc) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        uint8_t* sa = smem + stage * L.stage_bytes;
-        gather_block<kBf16, kLo, 8>(P.src, P.g, P.Kreal, kc * kChunkK, kg, r0, rb, rt, ry, rx, sa, sa + L.a_bytes);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[stage]);
+        const uint32_t sa = smem_base + stage * L.stage_bytes;
+        gather_block_async<kLo, 4>(P.src, P.g, P.Kreal, kc * kChunkK, ck, r0, rb, rt, ry, rx, sa, sa + L.a_bytes);
+        cp_async_commit();
+        if (prev_stage >= 0) {
+          // the previous chunk has landed once at most one group (this one) is still in flight
+          cp_async_wait<1>();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[prev_stage]);
+        }
+        prev_stage = (int)stage;
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
+    }
+    if (prev_stage >= 0) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[prev_stage]);
     }
   } else if (warp == 13) {
     // ===================== weight loader (bulk copies) =====================
@@ -253,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
         const int n_tile = tile % P.n_tiles;
         for (int kc = 0; kc < nkc; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sb = smem + stage * L.stage_bytes + (kLo ? 2u : 1u) * L.a_bytes;
+          uint8_t* sb = smem + stage * L.stage_bytes + copies * L.a_bytes;
           const uint8_t* src =
               reinterpret_cast<const uint8_t*>(P.wpk) + ((size_t)n_tile * nkc + kc) * (size_t)(2u * L.b_bytes);
           mbar_arrive_expect_tx(&full_bar[stage], bytes);
@@ -264,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
     }
   } else if (warp == 12) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc(kBf16 ? 1u : 0u, 0u, 0u, kTileM, (uint32_t)P.BN);
+    const uint32_t idesc = make_idesc(P.a_bf16 ? 1u : 0u, P.b_bf16 ? 1u : 0u, 0u, 0u, kTileM, (uint32_t)P.BN);
     uint32_t stage = 0, phase = 0;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -313,6 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row_base = m_tile * kTileM + warp * 32;
+      const int rows_here = min(32, M - row_base);
       for (int c0 = 0; c0 < P.BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 256u + (uint32_t)c0, v);
@@ -321,21 +296,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
         for (int j = 0; j < 32; ++j) my_stage[lane * kStagePitch + j] = __uint_as_float(v[j]);
         __syncwarp();
         const int col = n_tile * P.BN + c0 + lane;  // global output channel handled by this lane
-        const bool col_ok = col < P.N && (c0 + lane) < P.BN;
+        const bool col_ok = col < P.N;
         const float us = (P.wunscale != nullptr && col_ok) ? __ldg(P.wunscale + n_tile * P.BN + c0 + lane) : 1.f;
         float s1 = 0.f, s2 = 0.f;
-        if (col_ok) {
-          float* dcol = P.dst + P.dst_coff + col;
+        if (col_ok && rows_here > 0) {
+          float* d = P.dst + (size_t)row_base * P.dst_ld + P.dst_coff + col;
+          if (P.accumulate) {
+            for (int r = 0; r < rows_here; ++r, d += P.dst_ld) {
+              const float val = my_stage[r * kStagePitch + lane] * us + *d;
+              *d = val;
+            }
+          } else {
 #pragma unroll 8
-          for (int r = 0; r < 32; ++r) {
-            const int m = row_base + r;
-            if (m < M) {
-              float val = my_stage[r * kStagePitch + lane] * us;
-              float* d = dcol + (size_t)m * P.dst_ld;
-              if (P.accumulate) val += *d;
+            for (int r = 0; r < rows_here; ++r, d += P.dst_ld) {
+              const float val = my_stage[r * kStagePitch + lane] * us;
               *d = val;
               s1 += val;
-              s2 += val * val;
+              s2 = fmaf(val, val, s2);
             }
           }
           if (P.stats_sum != nullptr) {
@@ -362,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
   __syncthreads();
   if (warp == 13) {
     tc_fence_after();
+    __syncwarp();
     tmem_dealloc<512>(tmem_base);
   }
 }
@@ -387,7 +365,7 @@ __host__ __device__ inline WgradSmemLayout wgrad_smem_layout(int BNk, int npass)
   L.a_bytes = (uint32_t)(BNk / 64) * kWgPx * 128u;
   L.stage_bytes = copies * (L.dy_bytes + L.a_bytes);
   uint32_t st = (227u * 1024u - 2048u) / L.stage_bytes;
-  if (st > 6) st = 6;
+  if (st > (uint32_t)kMaxStages) st = kMaxStages;
   L.stages = st;
   L.off_bars = L.stages * L.stage_bytes;
   L.total = L.off_bars + 256u + 1024u;
@@ -401,7 +379,7 @@ __host__ __device__ inline int wgrad_bnk(int Kreal) {
   return ((w + 63) / 64) * 64;
 }
 
-template <bool kBf16, int kNPass>
+template <int kNPass>
 __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgrad_t P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -427,15 +405,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
   const int ch_end = min(chunks_total, ch_begin + chunks_per);
   const int nch = max(0, ch_end - ch_begin);
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.off_bars);  // [6]
-  uint64_t* empty_bar = full_bar + 6;
-  uint64_t* tfull_bar = empty_bar + 6;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.off_bars);  // [kMaxStages]
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tfull_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (uint32_t s = 0; s < 6; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&full_bar[s], kProducerWarps);
       mbar_init(&empty_bar[s], 1);
     }
@@ -450,43 +428,56 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
 
   if (warp >= kEpiWarps && warp < kEpiWarps + kProducerWarps) {
     const int pt = threadIdx.x - kEpiWarps * 32;
-    const int kg = pt & 15;
-    const int r0 = pt >> 4;  // rows r0 + 16*i, i < 4
+    const int ck = pt & 7;
+    const int r0 = pt >> 3;  // rows r0 + 32*i, i < 2
+    const uint32_t smem_base = smem_u32(smem);
     uint32_t stage = 0, phase = 0;
+    int prev_stage = -1;
     coclr_geom_t ident;
     ident.kt = ident.kh = ident.kw = 1;
     ident.st = ident.sh = ident.sw = 1;
     ident.pt = ident.ph = ident.pw = 0;
     ident.transposed = 0;
     for (int ch = ch_begin; ch < ch_begin + nch; ++ch) {
-      int rb[4], rt[4], ry[4], rx[4];    // source-space bases for the activation gather
-      int qb[4], qt[4], qy[4], qx[4];    // plain destination coordinates for dY
+      int rb[2], rt[2], ry[2], rx[2];    // source-space bases for the activation gather
+      int qb[2], qt[2], qy[2], qx[2];    // plain destination coordinates for dY
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = ch * kWgPx + r0 + 16 * i;
+      for (int i = 0; i < 2; ++i) {
+        const int m = ch * kWgPx + r0 + 32 * i;
         row_coords(P.g, P.Td, P.Hd, P.Wd, M, m, rb[i], rt[i], ry[i], rx[i]);
         row_coords(ident, P.Td, P.Hd, P.Wd, M, m, qb[i], qt[i], qy[i], qx[i]);
       }
       mbar_wait(&empty_bar[stage], phase ^ 1u);
-      uint8_t* s_dy = smem + stage * L.stage_bytes;
-      uint8_t* s_a = s_dy + (kLo ? 2u : 1u) * L.dy_bytes;
+      const uint32_t s_dy = smem_base + stage * L.stage_bytes;
+      const uint32_t s_a = s_dy + (kLo ? 2u : 1u) * L.dy_bytes;
       // dY: 2 blocks of 64 output channels
 #pragma unroll
       for (int blk = 0; blk < 2; ++blk) {
-        gather_block<kBf16, kLo, 4>(P.dy, ident, P.dy.C, c_tile * 128 + blk * 64, kg, r0, qb, qt, qy, qx,
-                                    s_dy + blk * (kWgPx * 128), s_dy + L.dy_bytes + blk * (kWgPx * 128));
+        gather_block_async<kLo, 2>(P.dy, ident, P.dy.C, c_tile * 128 + blk * 64, ck, r0, qb, qt, qy, qx,
+                                   s_dy + blk * (kWgPx * 128), s_dy + L.dy_bytes + blk * (kWgPx * 128));
       }
       for (int blk = 0; blk < BNk / 64; ++blk) {
-        gather_block<kBf16, kLo, 4>(P.src, P.g, Kreal, k_tile * BNk + blk * 64, kg, r0, rb, rt, ry, rx,
-                                    s_a + blk * (kWgPx * 128), s_a + L.a_bytes + blk * (kWgPx * 128));
+        gather_block_async<kLo, 2>(P.src, P.g, Kreal, k_tile * BNk + blk * 64, ck, r0, rb, rt, ry, rx,
+                                   s_a + blk * (kWgPx * 128), s_a + L.a_bytes + blk * (kWgPx * 128));
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[stage]);
+      cp_async_commit();
+      if (prev_stage >= 0) {
+        cp_async_wait<1>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[prev_stage]);
+      }
+      prev_stage = (int)stage;
       if (++stage == nstages) { stage = 0; phase ^= 1u; }
     }
+    if (prev_stage >= 0) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[prev_stage]);
+    }
   } else if (warp == 12) {
-    const uint32_t idesc = make_idesc(kBf16 ? 1u : 0u, 1u, 1u, 128u, (uint32_t)BNk);
+    const uint32_t idesc = make_idesc(P.dy_bf16 ? 1u : 0u, P.src_bf16 ? 1u : 0u, 1u, 1u, 128u, (uint32_t)BNk);
     uint32_t stage = 0, phase = 0;
     for (int ch = 0; ch < nch; ++ch) {
       mbar_wait(&full_bar[stage], phase);
@@ -545,6 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
   __syncthreads();
   if (warp == 13) {
     tc_fence_after();
+    __syncwarp();
     tmem_dealloc<256>(tmem_base);
   }
 }
@@ -642,37 +634,40 @@ extern "C" int coclr_pack_weights(const coclr_pack_t* p, coclr_stream_t stream) 
   return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
 }
 
-template <bool B, int NP>
+static bool src_ok(const coclr_src_t& s, int need_lo) {
+  if (!s.hi || (need_lo && !s.lo)) return false;
+  if (s.C % 8 != 0 || s.ld % 8 != 0 || s.coff % 8 != 0) return false;  // 16-byte cp.async granules
+  if (((uintptr_t)s.hi & 15) || ((uintptr_t)s.lo & 15)) return false;
+  return true;
+}
+
+template <int NP>
 static int launch_conv(const coclr_conv_t& P, int num_sms, cudaStream_t s) {
   const int M = P.B * P.Td * P.Hd * P.Wd;
   const int m_tiles = (M + kTileM - 1) / kTileM;
   const int total = m_tiles * P.n_tiles;
   const ConvSmemLayout L = conv_smem_layout(P.BN, P.n_tiles, NP, P.stats_sum != nullptr);
   if (L.stages < 2) return COCLR_E_ARG;
-  cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<B, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+  cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return COCLR_E_LAUNCH;
   const int grid = total < num_sms ? total : num_sms;
-  conv_igemm_kernel<B, NP><<<grid, kThreads, L.total, s>>>(P);
+  conv_igemm_kernel<NP><<<grid, kThreads, L.total, s>>>(P);
   return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
 }
 
 extern "C" int coclr_conv_igemm(const coclr_conv_t* p, int num_sms, coclr_stream_t stream) {
-  if (!p || !p->src.ptr || !p->wpk || !p->dst) return COCLR_E_ARG;
-  if (p->src.C % 4 != 0 || p->src.ld % 4 != 0 || p->src.coff % 4 != 0) return COCLR_E_ARG;
+  if (!p || !p->wpk || !p->dst) return COCLR_E_ARG;
+  if (!src_ok(p->src, p->npass > 1)) return COCLR_E_ARG;
   if (p->BN % 32 != 0 || p->BN > 256 || p->BN < 32 || p->n_tiles < 1) return COCLR_E_ARG;
   if (p->Kreal != p->g.kt * p->g.kh * p->g.kw * p->src.C) return COCLR_E_ARG;
   if ((p->g.st != 1 && p->g.st != 2) || (p->g.sh != 1 && p->g.sh != 2) || (p->g.sw != 1 && p->g.sw != 2))
     return COCLR_E_ARG;
   if (num_sms <= 0) return COCLR_E_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  if (p->bf16) {
-    return p->npass > 1 ? launch_conv<true, 3>(*p, num_sms, s) : launch_conv<true, 1>(*p, num_sms, s);
-  } else {
-    return p->npass > 1 ? launch_conv<false, 3>(*p, num_sms, s) : launch_conv<false, 1>(*p, num_sms, s);
-  }
+  return p->npass > 1 ? launch_conv<3>(*p, num_sms, s) : launch_conv<1>(*p, num_sms, s);
 }
 
-template <bool B, int NP>
+template <int NP>
 static int launch_wgrad(const coclr_wgrad_t& P, cudaStream_t s) {
   const int taps = P.g.kt * P.g.kh * P.g.kw;
   const int Kreal = taps * P.src.C;
@@ -681,22 +676,17 @@ static int launch_wgrad(const coclr_wgrad_t& P, cudaStream_t s) {
   const int c_tiles = (P.Cout + 127) / 128;
   const WgradSmemLayout L = wgrad_smem_layout(BNk, NP);
   if (L.stages < 2) return COCLR_E_ARG;
-  cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<B, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+  cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return COCLR_E_LAUNCH;
   const int grid = k_tiles * c_tiles * P.splits;
-  conv_wgrad_kernel<B, NP><<<grid, kThreads, L.total, s>>>(P);
+  conv_wgrad_kernel<NP><<<grid, kThreads, L.total, s>>>(P);
   return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
 }
 
 extern "C" int coclr_conv_wgrad(const coclr_wgrad_t* p, coclr_stream_t stream) {
-  if (!p || !p->src.ptr || !p->dy.ptr || !p->dw) return COCLR_E_ARG;
-  if (p->src.C % 4 != 0 || p->src.ld % 4 != 0 || p->src.coff % 4 != 0) return COCLR_E_ARG;
-  if (p->dy.C % 4 != 0 || p->dy.ld % 4 != 0 || p->dy.coff % 4 != 0) return COCLR_E_ARG;
+  if (!p || !p->dw) return COCLR_E_ARG;
+  if (!src_ok(p->src, p->npass > 1) || !src_ok(p->dy, p->npass > 1)) return COCLR_E_ARG;
   if (p->splits < 1 || p->g.transposed) return COCLR_E_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  if (p->bf16) {
-    return p->npass > 1 ? launch_wgrad<true, 3>(*p, s) : launch_wgrad<true, 1>(*p, s);
-  } else {
-    return p->npass > 1 ? launch_wgrad<false, 3>(*p, s) : launch_wgrad<false, 1>(*p, s);
-  }
+  return p->npass > 1 ? launch_wgrad<3>(*p, s) : launch_wgrad<1>(*p, s);
 }

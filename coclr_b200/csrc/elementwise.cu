@@ -1,7 +1,7 @@
-// HBM-bound kernels around the convolutions: BatchNorm finalize / backward, max-pooling, global
-// average pooling, input packing, L2-normalise, momentum (EMA) update, queue enqueue, Adam.
-// All activations are channels-last fp32 rows [pixels, ld]; channel counts are multiples of 4 and
-// every kernel moves float4 per thread with consecutive threads on consecutive addresses.
+// HBM-bound kernels around the convolutions: BatchNorm finalize / apply+split / backward, max-pooling,
+// global average pooling, input packing, L2-normalise, momentum (EMA) update, queue enqueue, Adam.
+// Activations are channels-last rows; channel counts are multiples of 8 for the 16-bit planes and every
+// kernel moves 8-16 bytes per thread with consecutive threads on consecutive addresses.
 #include "common.cuh"
 #include "coclr_b200.h"
 
@@ -10,24 +10,44 @@ namespace coclr {
 COCLR_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 COCLR_DEVINL void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
-COCLR_DEVINL float4 affine_relu(float4 v, float4 sc, float4 sh, int relu) {
-  v.x = fmaf(v.x, sc.x, sh.x);
-  v.y = fmaf(v.y, sc.y, sh.y);
-  v.z = fmaf(v.z, sc.z, sh.z);
-  v.w = fmaf(v.w, sc.w, sh.w);
-  if (relu) {
-    v.x = fmaxf(v.x, 0.f);
-    v.y = fmaxf(v.y, 0.f);
-    v.z = fmaxf(v.z, 0.f);
-    v.w = fmaxf(v.w, 0.f);
+COCLR_DEVINL float h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+
+// 4 consecutive channels of an fp16 hi/lo plane pair -> fp32 values (hi + lo)
+COCLR_DEVINL float4 ld_pair4(const uint16_t* hi, const uint16_t* lo, size_t off) {
+  const uint2 h = *reinterpret_cast<const uint2*>(hi + off);
+  float4 v;
+  v.x = h2f((uint16_t)(h.x & 0xffff));
+  v.y = h2f((uint16_t)(h.x >> 16));
+  v.z = h2f((uint16_t)(h.y & 0xffff));
+  v.w = h2f((uint16_t)(h.y >> 16));
+  if (lo != nullptr) {
+    const uint2 l = *reinterpret_cast<const uint2*>(lo + off);
+    v.x += h2f((uint16_t)(l.x & 0xffff));
+    v.y += h2f((uint16_t)(l.x >> 16));
+    v.z += h2f((uint16_t)(l.y & 0xffff));
+    v.w += h2f((uint16_t)(l.y >> 16));
   }
   return v;
 }
 
+template <bool kBf16>
+COCLR_DEVINL void st_pair4(uint16_t* hi, uint16_t* lo, size_t off, float4 v) {
+  uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+  split2<kBf16>(v.x, h0, l0);
+  split2<kBf16>(v.y, h1, l1);
+  split2<kBf16>(v.z, h2, l2);
+  split2<kBf16>(v.w, h3, l3);
+  *reinterpret_cast<uint2*>(hi + off) =
+      make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+  if (lo != nullptr)
+    *reinterpret_cast<uint2*>(lo + off) =
+        make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+}
+
 // ------------------------------------------------------------------------------------------------
-// BatchNorm finalize: per-channel sums -> (scale, shift) for the consumer prologue, saved
-// (mean, rstd) for backward, running-stat update.  nn.BatchNorm3d train-mode semantics
-// (backbone/s3dg.py:16,46-47): biased variance for normalisation, unbiased for running_var.
+// BatchNorm finalize: per-channel sums -> (scale, shift), saved (mean, rstd), running-stat update.
+// nn.BatchNorm3d train-mode semantics (backbone/s3dg.py:16,46-47): biased variance for normalisation,
+// unbiased for running_var.
 // ------------------------------------------------------------------------------------------------
 __global__ void bn_finalize_kernel(const coclr_bn_finalize_t P) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,12 +67,42 @@ __global__ void bn_finalize_kernel(const coclr_bn_finalize_t P) {
     mean = P.running_mean[c];
     var = P.running_var[c];
   }
-  const float rstd_exact = 1.f / sqrtf(var + P.eps);
-  const float sc = P.gamma[c] * rstd_exact;
+  const float rstd = 1.f / sqrtf(var + P.eps);
+  const float sc = P.gamma[c] * rstd;
   P.scale[c] = sc;
   P.shift[c] = P.beta[c] - mean * sc;
   if (P.save_mean) P.save_mean[c] = mean;
-  if (P.save_rstd) P.save_rstd[c] = rstd_exact;
+  if (P.save_rstd) P.save_rstd[c] = rstd;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm-apply + ReLU + hi/lo split: fp32 rows -> 16-bit operand planes (one read, one write)
+// ------------------------------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void __launch_bounds__(256) affine_split_kernel(const coclr_split_t P) {
+  const int C4 = P.C >> 2;
+  const long total = P.M * C4;
+  uint16_t* hi = reinterpret_cast<uint16_t*>(P.hi);
+  uint16_t* lo = reinterpret_cast<uint16_t*>(P.lo);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / C4;
+    const int c = (int)(i - r * C4) * 4;
+    float4 v = ld4(P.x + r * P.ld + P.coff + c);
+    if (P.scale != nullptr) {
+      const float4 sc = ld4(P.scale + c), sh = ld4(P.shift + c);
+      v.x = fmaf(v.x, sc.x, sh.x);
+      v.y = fmaf(v.y, sc.y, sh.y);
+      v.z = fmaf(v.z, sc.z, sh.z);
+      v.w = fmaf(v.w, sc.w, sh.w);
+    }
+    if (P.relu) {
+      v.x = fmaxf(v.x, 0.f);
+      v.y = fmaxf(v.y, 0.f);
+      v.z = fmaxf(v.z, 0.f);
+      v.w = fmaxf(v.w, 0.f);
+    }
+    st_pair4<kBf16>(hi, lo, (size_t)(r * P.out_ld + P.out_coff + c), v);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -106,8 +156,8 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_reduce_kernel(const coclr_
   }
 }
 
-// BN backward, phase 2 (in place on dA): dY = scale * (dz - s1/n - xhat * s2/n); block 0 also
-// writes dgamma = s2, dbeta = s1.
+// BN backward, phase 2: dY = scale * (dz - s1/n - xhat * s2/n) -> bf16 hi/lo planes; block 0 also
+// accumulates dgamma += s2, dbeta += s1.
 __global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(const coclr_bn_bwd_t P) {
   const int C4 = P.C >> 2;
   const int A = (kColThreads / C4) * C4;
@@ -129,13 +179,15 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(const coclr_b
       if (P.dbeta) P.dbeta[c + j] += (float)s1;
     }
   }
+  uint16_t* hi = reinterpret_cast<uint16_t*>(P.dy_hi);
+  uint16_t* lo = reinterpret_cast<uint16_t*>(P.dy_lo);
   const long rows_per = ((long)P.M + gridDim.x - 1) / gridDim.x;
   const long r_begin = (long)blockIdx.x * rows_per;
   const long r_end = min((long)P.M, r_begin + rows_per);
   for (long r = r_begin + rs; r < r_end; r += R) {
-    const float4 y = ld4(P.y + r * P.ld + P.coff + c);
-    float* dp = P.dA + r * P.ld + P.coff + c;
-    const float4 da = ld4(dp);
+    const size_t off = (size_t)(r * P.ld + P.coff + c);
+    const float4 y = ld4(P.y + off);
+    const float4 da = ld4(P.dA + off);
     float4 o;
     {
       const float dz = (!P.relu || fmaf(y.x, sc.x, sh.x) > 0.f) ? da.x : 0.f;
@@ -153,12 +205,12 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(const coclr_b
       const float dz = (!P.relu || fmaf(y.w, sc.w, sh.w) > 0.f) ? da.w : 0.f;
       o.w = sc.w * (dz - m1[3] - ((y.w - mu.w) * rs4.w) * m2[3]);
     }
-    st4(dp, o);
+    st_pair4<true>(hi, lo, off, o);
   }
 }
 
 // bias + ReLU backward for the projection head (model/pretrain.py:52-53): in place dz = dA*[h+b>0],
-// dbias = sum_rows dz.  One CTA, rows are few (the batch).
+// dbias += sum_rows dz.  Rows are few (the batch).
 __global__ void bias_relu_bwd_kernel(const float* h, const float* bias, float* dA, float* dbias, int M, int C) {
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -174,11 +226,19 @@ __global__ void bias_relu_bwd_kernel(const float* h, const float* bias, float* d
 
 // ------------------------------------------------------------------------------------------------
 // MaxPool3d (nn.MaxPool3d; backbone/s3dg.py:105,151,162,173,190): -inf padding, first maximum wins.
-// The input affine+ReLU (pending BatchNorm of the producer) is applied on load; the output is final.
+// Input and output are fp16 hi/lo planes (the arg-max element's pair is copied, so no re-rounding).
+// Compile-time window/stride for the four shapes S3D uses (0 = take the run-time value).
 // ------------------------------------------------------------------------------------------------
-__global__ void maxpool_fwd_kernel(const coclr_pool_t P) {
+template <int KT, int KH, int KW, int ST, int SH, int SW>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const coclr_pool_t P) {
+  const int kt = KT ? KT : P.g.kt, kh = KH ? KH : P.g.kh, kw = KW ? KW : P.g.kw;
+  const int st = ST ? ST : P.g.st, sh = SH ? SH : P.g.sh, sw = SW ? SW : P.g.sw;
   const int C4 = P.C >> 2;
   const long total = (long)P.B * P.To * P.Ho * P.Wo * C4;
+  const uint16_t* xh = reinterpret_cast<const uint16_t*>(P.x_hi);
+  const uint16_t* xl = reinterpret_cast<const uint16_t*>(P.x_lo);
+  uint16_t* yh = reinterpret_cast<uint16_t*>(P.y_hi);
+  uint16_t* yl = reinterpret_cast<uint16_t*>(P.y_lo);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int cg = (int)(i % C4);
     long r = i / C4;
@@ -187,35 +247,54 @@ __global__ void maxpool_fwd_kernel(const coclr_pool_t P) {
     const int to = (int)(r % P.To);
     const int b = (int)(r / P.To);
     const int c = cg * 4;
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (P.scale) { sc = ld4(P.scale + c); sh = ld4(P.shift + c); }
-    float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    uchar4 bi = make_uchar4(0, 0, 0, 0);
-    int tap = 0;
-    for (int a = 0; a < P.g.kt; ++a) {
-      const int ti = to * P.g.st - P.g.pt + a;
-      for (int bb = 0; bb < P.g.kh; ++bb) {
-        const int yi = yo * P.g.sh - P.g.ph + bb;
-        for (int cc = 0; cc < P.g.kw; ++cc, ++tap) {
-          const int xi = xo * P.g.sw - P.g.pw + cc;
-          if ((unsigned)ti >= (unsigned)P.Ti || (unsigned)yi >= (unsigned)P.Hi || (unsigned)xi >= (unsigned)P.Wi) continue;
-          float4 v = ld4(P.x + ((((long)b * P.Ti + ti) * P.Hi + yi) * P.Wi + xi) * P.ldx + P.x_coff + c);
-          if (P.scale) v = affine_relu(v, sc, sh, P.relu);
-          if (v.x > best.x) { best.x = v.x; bi.x = (unsigned char)tap; }
-          if (v.y > best.y) { best.y = v.y; bi.y = (unsigned char)tap; }
-          if (v.z > best.z) { best.z = v.z; bi.z = (unsigned char)tap; }
-          if (v.w > best.w) { best.w = v.w; bi.w = (unsigned char)tap; }
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    uint16_t bh[4] = {0xfc00, 0xfc00, 0xfc00, 0xfc00}, bl[4] = {0, 0, 0, 0};  // fp16 -inf
+    unsigned char bi[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < kt; ++a) {
+      const int ti = to * st - P.g.pt + a;
+      if ((unsigned)ti >= (unsigned)P.Ti) continue;
+#pragma unroll
+      for (int bb = 0; bb < kh; ++bb) {
+        const int yi = yo * sh - P.g.ph + bb;
+        if ((unsigned)yi >= (unsigned)P.Hi) continue;
+#pragma unroll
+        for (int cc = 0; cc < kw; ++cc) {
+          const int xi = xo * sw - P.g.pw + cc;
+          if ((unsigned)xi >= (unsigned)P.Wi) continue;
+          const int tap = (a * kh + bb) * kw + cc;
+          const size_t off = ((((size_t)b * P.Ti + ti) * P.Hi + yi) * P.Wi + xi) * P.ldx + P.x_coff + c;
+          const uint2 h = *reinterpret_cast<const uint2*>(xh + off);
+          uint2 l = make_uint2(0u, 0u);
+          if (xl != nullptr) l = *reinterpret_cast<const uint2*>(xl + off);
+          const uint16_t hh[4] = {(uint16_t)(h.x & 0xffff), (uint16_t)(h.x >> 16), (uint16_t)(h.y & 0xffff),
+                                  (uint16_t)(h.y >> 16)};
+          const uint16_t ll[4] = {(uint16_t)(l.x & 0xffff), (uint16_t)(l.x >> 16), (uint16_t)(l.y & 0xffff),
+                                  (uint16_t)(l.y >> 16)};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float v = h2f(hh[j]) + h2f(ll[j]);
+            if (v > best[j]) { best[j] = v; bh[j] = hh[j]; bl[j] = ll[j]; bi[j] = (unsigned char)tap; }
+          }
         }
       }
     }
-    const long o = ((((long)b * P.To + to) * P.Ho + yo) * P.Wo + xo);
-    st4(P.y + o * P.ldy + P.y_coff + c, best);
-    if (P.idx) *reinterpret_cast<uchar4*>(P.idx + o * P.C + c) = bi;
+    const size_t o = ((((size_t)b * P.To + to) * P.Ho + yo) * P.Wo + xo);
+    const size_t oo = o * P.ldy + P.y_coff + c;
+    *reinterpret_cast<uint2*>(yh + oo) =
+        make_uint2((uint32_t)bh[0] | ((uint32_t)bh[1] << 16), (uint32_t)bh[2] | ((uint32_t)bh[3] << 16));
+    if (yl != nullptr)
+      *reinterpret_cast<uint2*>(yl + oo) =
+          make_uint2((uint32_t)bl[0] | ((uint32_t)bl[1] << 16), (uint32_t)bl[2] | ((uint32_t)bl[3] << 16));
+    if (P.idx) *reinterpret_cast<uchar4*>(P.idx + o * P.C + c) = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
   }
 }
 
 // gather form of the backward: dX[in] (+)= sum over windows whose arg-max is `in` of dY[out]
-__global__ void maxpool_bwd_kernel(const coclr_pool_t P) {
+template <int KT, int KH, int KW, int ST, int SH, int SW>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const coclr_pool_t P) {
+  const int kt = KT ? KT : P.g.kt, kh = KH ? KH : P.g.kh, kw = KW ? KW : P.g.kw;
+  const int st = ST ? ST : P.g.st, sh = SH ? SH : P.g.sh, sw = SW ? SW : P.g.sw;
   const int C4 = P.C >> 2;
   const long total = (long)P.B * P.Ti * P.Hi * P.Wi * C4;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -227,24 +306,29 @@ __global__ void maxpool_bwd_kernel(const coclr_pool_t P) {
     const int b = (int)(r / P.Ti);
     const int c = cg * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int tap = 0;
-    for (int a = 0; a < P.g.kt; ++a) {
+#pragma unroll
+    for (int a = 0; a < kt; ++a) {
       int nt = ti + P.g.pt - a;
-      const bool vt = nt >= 0 && (nt % P.g.st) == 0 && (nt / P.g.st) < P.To;
-      nt /= P.g.st;
-      for (int bb = 0; bb < P.g.kh; ++bb) {
+      if (nt < 0 || (nt % st) != 0) continue;
+      nt /= st;
+      if (nt >= P.To) continue;
+#pragma unroll
+      for (int bb = 0; bb < kh; ++bb) {
         int ny = yi + P.g.ph - bb;
-        const bool vy = ny >= 0 && (ny % P.g.sh) == 0 && (ny / P.g.sh) < P.Ho;
-        ny /= P.g.sh;
-        for (int cc = 0; cc < P.g.kw; ++cc, ++tap) {
+        if (ny < 0 || (ny % sh) != 0) continue;
+        ny /= sh;
+        if (ny >= P.Ho) continue;
+#pragma unroll
+        for (int cc = 0; cc < kw; ++cc) {
           int nx = xi + P.g.pw - cc;
-          const bool vx = nx >= 0 && (nx % P.g.sw) == 0 && (nx / P.g.sw) < P.Wo;
-          nx /= P.g.sw;
-          if (!(vt && vy && vx)) continue;
-          const long o = ((((long)b * P.To + nt) * P.Ho + ny) * P.Wo + nx);
+          if (nx < 0 || (nx % sw) != 0) continue;
+          nx /= sw;
+          if (nx >= P.Wo) continue;
+          const int tap = (a * kh + bb) * kw + cc;
+          const size_t o = ((((size_t)b * P.To + nt) * P.Ho + ny) * P.Wo + nx);
           const uchar4 id = *reinterpret_cast<const uchar4*>(P.idx + o * P.C + c);
           if (id.x == tap || id.y == tap || id.z == tap || id.w == tap) {
-            const float4 d = ld4(P.dy + o * P.ldy + P.y_coff + c);
+            const float4 d = ld4(P.dy + o * P.C + c);
             if (id.x == tap) acc.x += d.x;
             if (id.y == tap) acc.y += d.y;
             if (id.z == tap) acc.z += d.z;
@@ -253,7 +337,7 @@ __global__ void maxpool_bwd_kernel(const coclr_pool_t P) {
         }
       }
     }
-    float* dp = P.dx + ((((long)b * P.Ti + ti) * P.Hi + yi) * P.Wi + xi) * P.ldx + P.x_coff + c;
+    float* dp = P.dx + ((((size_t)b * P.Ti + ti) * P.Hi + yi) * P.Wi + xi) * P.ldx + P.x_coff + c;
     if (P.accumulate) {
       const float4 old = ld4(dp);
       acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
@@ -263,25 +347,22 @@ __global__ void maxpool_bwd_kernel(const coclr_pool_t P) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// AdaptiveAvgPool3d((1,1,1)) over relu(scale*y+shift) (model/pretrain.py:51) and its backward
+// AdaptiveAvgPool3d((1,1,1)) (model/pretrain.py:51) over fp16 hi/lo planes, and its backward
 // ------------------------------------------------------------------------------------------------
-__global__ void avgpool_fwd_kernel(const float* x, int ld, int coff, const float* scale, const float* shift, int relu,
-                                   float* out, int B, int Pn, int C) {
+__global__ void avgpool_fwd_kernel(const uint16_t* xh, const uint16_t* xl, int ld, int coff, float* out, int B, int Pn,
+                                   int C) {
   const int C4 = C >> 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C4) return;
   const int cg = i % C4, b = i / C4;
   const int c = cg * 4;
-  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (scale) { sc = ld4(scale + c); sh = ld4(shift + c); }
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int p = 0; p < Pn; ++p) {
-    float4 v = ld4(x + ((long)b * Pn + p) * ld + coff + c);
-    if (scale) v = affine_relu(v, sc, sh, relu);
+    const float4 v = ld_pair4(xh, xl, ((size_t)b * Pn + p) * ld + coff + c);
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
   const float inv = 1.f / (float)Pn;
-  st4(out + (long)b * C + c, make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv));
+  st4(out + (size_t)b * C + c, make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv));
 }
 __global__ void avgpool_bwd_kernel(const float* dfeat, float* dA, int ld, int coff, int B, int Pn, int C) {
   const int C4 = C >> 2;
@@ -297,22 +378,30 @@ __global__ void avgpool_bwd_kernel(const float* dfeat, float* dA, int ld, int co
 }
 
 // ------------------------------------------------------------------------------------------------
-// clip packing: x[b, c, t, h, w] (c < 3, arbitrary batch stride: the reference's block[:, i]
-// .contiguous() copies, model/pretrain.py:149-150, are folded in) -> [b, thw, 4] with channel 3 = 0
+// clip packing: x[b, c, t, h, w] (c < Cin <= 8, arbitrary batch stride: the reference's block[:, i]
+// .contiguous() copies, model/pretrain.py:149-150, are folded in) -> fp16 hi/lo planes [b, thw, 8]
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_input_kernel(const float* x, long batch_stride, long chan_stride, int Cin, float* out, int B,
-                                  long thw, const long* __restrict__ batch_index) {
+__global__ void __launch_bounds__(256) pack_input_kernel(const float* x, long batch_stride, long chan_stride, int Cin,
+                                                         uint16_t* out_hi, uint16_t* out_lo, int B, long thw,
+                                                         const long* __restrict__ batch_index) {
   const long total = (long)B * thw;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long b = i / thw, p = i - b * thw;
     const long sb = batch_index ? batch_index[b] : b;  // shuffle-BN gather folded in (pretrain.py:124)
     const float* s = x + sb * batch_stride + p;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    v.x = s[0];
-    if (Cin > 1) v.y = s[chan_stride];
-    if (Cin > 2) v.z = s[2 * chan_stride];
-    if (Cin > 3) v.w = s[3 * chan_stride];
-    st4(out + i * 4, v);
+    uint16_t h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = j < Cin ? s[(long)j * chan_stride] : 0.f;
+      split2<false>(v, h[j], l[j]);
+    }
+    *reinterpret_cast<uint4*>(out_hi + i * 8) =
+        make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
+                   (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
+    if (out_lo != nullptr)
+      *reinterpret_cast<uint4*>(out_lo + i * 8) =
+          make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
+                     (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
   }
 }
 
@@ -418,8 +507,21 @@ extern "C" int coclr_bn_finalize(const coclr_bn_finalize_t* p, coclr_stream_t st
   return LAUNCH_OK();
 }
 
+extern "C" int coclr_affine_split(const coclr_split_t* p, int num_sms, coclr_stream_t stream) {
+  if (!p || !p->x || !p->hi || p->C % 4 || p->ld % 4 || p->coff % 4 || p->out_ld % 4 || p->out_coff % 4)
+    return COCLR_E_ARG;
+  const long total = p->M * (p->C / 4);
+  const int grid = grid_for(total, 256, num_sms * 16);
+  if (p->bf16)
+    affine_split_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+  else
+    affine_split_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+  return LAUNCH_OK();
+}
+
 extern "C" int coclr_bn_bwd(const coclr_bn_bwd_t* p, int num_sms, coclr_stream_t stream) {
-  if (!p || !p->y || !p->dA || !p->sums || p->C % 4 || p->C > 1024 || p->ld % 4 || p->coff % 4) return COCLR_E_ARG;
+  if (!p || !p->y || !p->dA || !p->sums || !p->dy_hi || p->C % 4 || p->C > 1024 || p->ld % 4 || p->coff % 4)
+    return COCLR_E_ARG;
   const int C4 = p->C / 4;
   const int R = kColThreads / C4;
   long slabs = ((long)p->M + (long)R * 16 - 1) / ((long)R * 16);
@@ -439,25 +541,49 @@ extern "C" int coclr_bias_relu_bwd(const float* h, const float* bias, float* dA,
   return LAUNCH_OK();
 }
 
+template <bool kBwd>
+static void launch_pool(const coclr_pool_t& p, long total, cudaStream_t s) {
+  const int grid = grid_for(total, 256, 148 * 32);
+  const coclr_geom_t& g = p.g;
+#define POOL_CASE(KT, KH, KW, ST, SH, SW)                                                 \
+  if (g.kt == KT && g.kh == KH && g.kw == KW && g.st == ST && g.sh == SH && g.sw == SW) { \
+    if (kBwd)                                                                             \
+      maxpool_bwd_kernel<KT, KH, KW, ST, SH, SW><<<grid, 256, 0, s>>>(p);                 \
+    else                                                                                  \
+      maxpool_fwd_kernel<KT, KH, KW, ST, SH, SW><<<grid, 256, 0, s>>>(p);                 \
+    return;                                                                               \
+  }
+  POOL_CASE(1, 3, 3, 1, 2, 2)
+  POOL_CASE(3, 3, 3, 1, 1, 1)
+  POOL_CASE(3, 3, 3, 2, 2, 2)
+  POOL_CASE(2, 2, 2, 2, 2, 2)
+#undef POOL_CASE
+  if (kBwd)
+    maxpool_bwd_kernel<0, 0, 0, 0, 0, 0><<<grid, 256, 0, s>>>(p);
+  else
+    maxpool_fwd_kernel<0, 0, 0, 0, 0, 0><<<grid, 256, 0, s>>>(p);
+}
+
 extern "C" int coclr_maxpool_fwd(const coclr_pool_t* p, coclr_stream_t stream) {
-  if (!p || !p->x || !p->y || p->C % 4 || p->ldx % 4 || p->ldy % 4) return COCLR_E_ARG;
+  if (!p || !p->x_hi || !p->y_hi || p->C % 4 || p->ldx % 4 || p->ldy % 4 || p->x_coff % 4 || p->y_coff % 4)
+    return COCLR_E_ARG;
   if (p->g.kt * p->g.kh * p->g.kw > 255) return COCLR_E_ARG;
   const long total = (long)p->B * p->To * p->Ho * p->Wo * (p->C / 4);
-  maxpool_fwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(*p);
+  launch_pool<false>(*p, total, (cudaStream_t)stream);
   return LAUNCH_OK();
 }
 extern "C" int coclr_maxpool_bwd(const coclr_pool_t* p, coclr_stream_t stream) {
   if (!p || !p->dx || !p->dy || !p->idx || p->C % 4) return COCLR_E_ARG;
   const long total = (long)p->B * p->Ti * p->Hi * p->Wi * (p->C / 4);
-  maxpool_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(*p);
+  launch_pool<true>(*p, total, (cudaStream_t)stream);
   return LAUNCH_OK();
 }
 
-extern "C" int coclr_avgpool_fwd(const float* x, int ld, int coff, const float* scale, const float* shift, int relu,
-                                 float* out, int B, int Pn, int C, coclr_stream_t stream) {
-  if (!x || !out || C % 4) return COCLR_E_ARG;
-  avgpool_fwd_kernel<<<(B * (C / 4) + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, ld, coff, scale, shift, relu, out,
-                                                                                B, Pn, C);
+extern "C" int coclr_avgpool_fwd(const void* x_hi, const void* x_lo, int ld, int coff, float* out, int B, int Pn, int C,
+                                 coclr_stream_t stream) {
+  if (!x_hi || !out || C % 4) return COCLR_E_ARG;
+  avgpool_fwd_kernel<<<(B * (C / 4) + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint16_t*>(x_hi), reinterpret_cast<const uint16_t*>(x_lo), ld, coff, out, B, Pn, C);
   return LAUNCH_OK();
 }
 extern "C" int coclr_avgpool_bwd(const float* dfeat, float* dA, int ld, int coff, int B, int Pn, int C,
@@ -468,11 +594,12 @@ extern "C" int coclr_avgpool_bwd(const float* dfeat, float* dA, int ld, int coff
   return LAUNCH_OK();
 }
 
-extern "C" int coclr_pack_input(const float* x, long batch_stride, long chan_stride, int Cin, float* out, int B,
-                                long thw, const long* batch_index, coclr_stream_t stream) {
-  if (!x || !out || Cin < 1 || Cin > 4) return COCLR_E_ARG;
-  pack_input_kernel<<<grid_for((long)B * thw, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(x, batch_stride,
-                                                                                             chan_stride, Cin, out, B, thw, batch_index);
+extern "C" int coclr_pack_input(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi, void* out_lo,
+                                int B, long thw, const long* batch_index, coclr_stream_t stream) {
+  if (!x || !out_hi || Cin < 1 || Cin > 8) return COCLR_E_ARG;
+  pack_input_kernel<<<grid_for((long)B * thw, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      x, batch_stride, chan_stride, Cin, reinterpret_cast<uint16_t*>(out_hi), reinterpret_cast<uint16_t*>(out_lo), B, thw,
+      batch_index);
   return LAUNCH_OK();
 }
 

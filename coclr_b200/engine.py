@@ -22,16 +22,16 @@ from .s3d_spec import s3d_stages, S3D_FEATURE_SIZE
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
-# name -> (fwd_npass, fwd_bf16, bwd_npass, bwd_bf16)
+# name -> (fwd_npass, fwd_bf16, bwd_npass): forward planes fp16 (hi/lo) or bf16; gradients are always bf16 planes
 PRECISIONS = {
-    "parity": (3, 0, 3, 1),   # fp16 hi/lo split forward (fp32-grade), bf16 hi/lo split backward
-    "fast": (1, 1, 1, 1),     # single-pass bf16 everywhere (does NOT meet the 1e-3 parity bar)
-    "mixed": (3, 0, 1, 1),    # fp32-grade forward, single-pass bf16 backward
+    "parity": (3, 0, 3),   # fp16 hi/lo split forward (fp32-grade), bf16 hi/lo split backward
+    "mixed": (3, 0, 1),    # fp32-grade forward (same logits/loss/queue as parity), single-pass bf16 backward
+    "fast": (1, 1, 1),     # single-pass bf16 everywhere (does NOT meet the 1e-3 parity bar)
 }
 
 
-def _round4(c):
-    return (c + 3) // 4 * 4
+def _round8(c):
+    return (c + 7) // 8 * 8
 
 
 # ---------------------------------------------------------------------------------------------
@@ -68,7 +68,7 @@ class Graph:
         self.first_channel = first_channel
         self.head_dim, self.feature_size = head_dim, feature_size
         pre = bb_prefix
-        x = self._tensor("input", _round4(first_channel), lambda d: d, pending=False)
+        x = self._tensor("input", _round8(first_channel), lambda d: d, pending=False)
         self.input = x
         first_conv = True
         for stg in stages:
@@ -254,8 +254,8 @@ class ParamStore:
 # shape-specific plan
 # ---------------------------------------------------------------------------------------------
 class _Act:
-    __slots__ = ("spec", "dims", "data", "grad", "scale", "shift", "mean", "rstd", "ssum", "ssq", "idx", "bsums",
-                 "grad_written", "M")
+    __slots__ = ("spec", "dims", "data", "pl", "grad", "dy", "scale", "shift", "mean", "rstd", "ssum", "ssq", "idx",
+                 "bsums", "grad_written", "M")
 
 
 class Plan:
@@ -268,7 +268,8 @@ class Plan:
         self.keep = []          # keeps ctypes structs / tensors alive
         self.fwd, self.bwd = [], []
         nsm = L.num_sms(dev)
-        fnp, fbf, bnp, bbf = PRECISIONS[eng.precision]
+        fnp, fbf, bnp = PRECISIONS[eng.precision]
+        need_lo = fnp > 1 or (with_backward and bnp > 1)
         # ---- activations ----
         acts = {}
         n_stat = sum(t.C for t in g.tensors if t.pending)
@@ -279,9 +280,12 @@ class Plan:
             a = _Act()
             a.spec, a.dims = t, t.dims_fn((T, H, W))
             a.M = B * a.dims[0] * a.dims[1] * a.dims[2]
-            a.data = torch.empty((B,) + a.dims + (t.C,), dtype=torch.float32, device=dev)
-            a.grad, a.idx, a.bsums, a.grad_written = None, None, None, False
+            shape = (B,) + a.dims + (t.C,)
+            a.pl = ops.Planes(shape, fbf, dev, lo=need_lo)          # what every consumer reads
+            a.data = a.grad = a.dy = a.idx = a.bsums = None
+            a.grad_written = False
             if t.pending:
+                a.data = torch.empty(shape, dtype=torch.float32, device=dev)   # raw conv output (pre-BN)
                 a.ssum = self.stats[so:so + t.C]
                 a.ssq = self.stats[n_stat + so:n_stat + so + t.C]
                 a.scale = self.aff[so:so + t.C]
@@ -292,17 +296,22 @@ class Plan:
             else:
                 a.ssum = a.ssq = a.scale = a.shift = a.mean = a.rstd = None
             if with_backward and t is not g.input:
-                a.grad = torch.empty_like(a.data)
+                a.grad = torch.empty(shape, dtype=torch.float32, device=dev)
+                if t.pending:
+                    a.dy = ops.Planes(shape, 1, dev, lo=bnp > 1)
             acts[t.index] = a
         self.acts = acts
         self.input = acts[g.input.index]
         st = eng.store
 
-        def src_of(a, C=None, grad=False):
-            sp = a.spec
-            return ops.make_src(a.grad if grad else a.data, 0, C or sp.C, a.dims[0], a.dims[1], a.dims[2],
-                                None if grad else a.scale, None if grad else a.shift,
-                                relu=(sp.relu and not grad))
+        def src_of(a):
+            return a.pl.src(0, a.spec.C, a.dims[0], a.dims[1], a.dims[2])
+
+        def split_op(x, planes, M, Cc, scale, shift, relu):
+            sp = L.Split(L.dptr(x), x.shape[-1], 0, Cc, M, L.dptr(scale), L.dptr(shift), int(bool(relu)),
+                         L.dptr(planes.hi), L.dptr(planes.lo), planes.ld, 0, planes.bf16)
+            self.keep.append(sp)
+            return (lib.coclr_affine_split, (C.byref(sp), nsm))
 
         # ---- forward ----
         for kind, it in g.items:
@@ -310,7 +319,7 @@ class Plan:
                 sa, da = acts[it.src.index], acts[it.dst.index]
                 geom = ops.Geometry(it.k, it.s, it.p)
                 pw = eng.packed_fwd[it.name]
-                cv = ops.make_conv(src_of(sa), geom.c(0), B, da.dims, pw, da.data, it.dst_coff,
+                cv = ops.make_conv(src_of(sa), fbf, geom.c(0), B, da.dims, pw, da.data, it.dst_coff,
                                    stats_sum=da.ssum[it.dst_coff:] if training else None,
                                    stats_sq=da.ssq[it.dst_coff:] if training else None, npass=fnp)
                 self.keep.append(cv)
@@ -320,8 +329,8 @@ class Plan:
                 geom = ops.Geometry(it.k, it.s, it.p)
                 if with_backward:
                     da.idx = torch.empty(da.M * it.dst.C, dtype=torch.uint8, device=dev)
-                pl = L.Pool(L.dptr(sa.data), it.src.C, 0, L.dptr(sa.scale), L.dptr(sa.shift), it.src.relu,
-                            L.dptr(da.data), it.dst.C, 0, L.dptr(da.idx), B, it.dst.C,
+                pl = L.Pool(L.dptr(sa.pl.hi), L.dptr(sa.pl.lo), it.src.C, 0, L.dptr(da.pl.hi), L.dptr(da.pl.lo),
+                            it.dst.C, 0, L.dptr(da.idx), B, it.dst.C,
                             sa.dims[0], sa.dims[1], sa.dims[2], da.dims[0], da.dims[1], da.dims[2], geom.c(0),
                             None, None, 0)
                 self.keep.append(pl)
@@ -339,28 +348,34 @@ class Plan:
                                   L.dptr(a.mean), L.dptr(a.rstd), it.C)
                 self.keep.append(bf)
                 self.fwd.append((lib.coclr_bn_finalize, (C.byref(bf),)))
+                self.fwd.append(split_op(a.data, a.pl, a.M, it.C, a.scale, a.shift, it.relu))
         # ---- head ----
         out = acts[g.backbone_out.index]
         self.backbone_out = out
         if g.head_dim is not None:
             fs, hd = g.feature_size, g.head_dim
             Pn = out.dims[0] * out.dims[1] * out.dims[2]
-            self.feat = torch.empty(B, 1, 1, 1, fs, dtype=torch.float32, device=dev)
-            self.h1 = torch.empty(B, 1, 1, 1, fs, dtype=torch.float32, device=dev)
-            self.h2 = torch.empty(B, 1, 1, 1, hd, dtype=torch.float32, device=dev)
-            self.q = torch.empty(B, hd, dtype=torch.float32, device=dev)
-            self.inv_norm = torch.empty(B, dtype=torch.float32, device=dev)
-            self.ones = torch.ones(fs, dtype=torch.float32, device=dev)
-            self.fwd.append((lib.coclr_avgpool_fwd, (L.dptr(out.data), out.spec.C, 0, L.dptr(out.scale), L.dptr(out.shift),
-                                                     out.spec.relu, L.dptr(self.feat), B, Pn, fs)))
+            f32 = dict(dtype=torch.float32, device=dev)
+            self.feat = torch.empty(B, 1, 1, 1, fs, **f32)
+            self.h1 = torch.empty(B, 1, 1, 1, fs, **f32)
+            self.h2 = torch.empty(B, 1, 1, 1, hd, **f32)
+            self.q = torch.empty(B, hd, **f32)
+            self.inv_norm = torch.empty(B, **f32)
+            self.ones = torch.ones(fs, **f32)
+            self.feat_pl = ops.Planes((B, 1, 1, 1, fs), fbf, dev, lo=need_lo)
+            self.h1_pl = ops.Planes((B, 1, 1, 1, fs), fbf, dev, lo=need_lo)
+            self.fwd.append((lib.coclr_avgpool_fwd, (L.dptr(out.pl.hi), L.dptr(out.pl.lo), out.spec.C, 0,
+                                                     L.dptr(self.feat), B, Pn, fs)))
+            self.fwd.append(split_op(self.feat, self.feat_pl, B, fs, None, None, False))
             one = ops.Geometry((1, 1, 1))
-            s_feat = ops.make_src(self.feat, 0, fs, 1, 1, 1)
             b2, b4 = st.view("2.bias"), st.view("4.bias")
-            s_h1 = ops.make_src(self.h1, 0, fs, 1, 1, 1, self.ones, b2, relu=True)
-            c1 = ops.make_conv(s_feat, one.c(0), B, (1, 1, 1), eng.packed_fwd["2"], self.h1, npass=fnp)
-            c2 = ops.make_conv(s_h1, one.c(0), B, (1, 1, 1), eng.packed_fwd["4"], self.h2, npass=fnp)
+            s_feat = self.feat_pl.src(0, fs, 1, 1, 1)
+            s_h1 = self.h1_pl.src(0, fs, 1, 1, 1)
+            c1 = ops.make_conv(s_feat, fbf, one.c(0), B, (1, 1, 1), eng.packed_fwd["2"], self.h1, npass=fnp)
+            c2 = ops.make_conv(s_h1, fbf, one.c(0), B, (1, 1, 1), eng.packed_fwd["4"], self.h2, npass=fnp)
             self.keep += [c1, c2, s_feat, s_h1]
             self.fwd.append((lib.coclr_conv_igemm, (C.byref(c1), nsm)))
+            self.fwd.append(split_op(self.h1, self.h1_pl, B, fs, self.ones, b2, True))   # bias + ReLU
             self.fwd.append((lib.coclr_conv_igemm, (C.byref(c2), nsm)))
             self.fwd.append((lib.coclr_l2norm_fwd, (L.dptr(self.h2), L.dptr(b4), L.dptr(self.q), L.dptr(self.inv_norm), B, hd)))
         if not with_backward:
@@ -368,28 +383,31 @@ class Plan:
         # ---- backward ----
         bw = self.bwd
         if g.head_dim is not None:
-            self.dq = torch.empty(B, hd, dtype=torch.float32, device=dev)
-            self.dh2 = torch.empty(B, 1, 1, 1, hd, dtype=torch.float32, device=dev)
-            self.dh1 = torch.empty(B, 1, 1, 1, fs, dtype=torch.float32, device=dev)
-            self.dfeat = torch.empty(B, 1, 1, 1, fs, dtype=torch.float32, device=dev)
+            self.dq = torch.empty(B, hd, **f32)
+            self.dh2 = torch.empty(B, 1, 1, 1, hd, **f32)
+            self.dh1 = torch.empty(B, 1, 1, 1, fs, **f32)
+            self.dfeat = torch.empty(B, 1, 1, 1, fs, **f32)
+            self.dh2_pl = ops.Planes((B, 1, 1, 1, hd), 1, dev, lo=bnp > 1)
+            self.dh1_pl = ops.Planes((B, 1, 1, 1, fs), 1, dev, lo=bnp > 1)
             bw.append((lib.coclr_l2norm_bwd, (L.dptr(self.q), L.dptr(self.dq), L.dptr(self.inv_norm), L.dptr(self.dh2),
                                               L.dptr(st.view("4.bias", grad=True)), B, hd)))
-            s_dh2 = ops.make_src(self.dh2, 0, hd, 1, 1, 1)
-            wg2 = L.Wgrad(s_h1, one.c(0), s_dh2, B, 1, 1, 1, hd, fs, L.dptr(st.view("4.weight", grad=True)), bnp, bbf, 1)
-            dg2 = ops.make_conv(s_dh2, one.c(1), B, (1, 1, 1), eng.packed_bwd["4"], self.dh1, npass=bnp)
-            s_dh1 = ops.make_src(self.dh1, 0, fs, 1, 1, 1)
-            wg1 = L.Wgrad(s_feat, one.c(0), s_dh1, B, 1, 1, 1, fs, fs, L.dptr(st.view("2.weight", grad=True)), bnp, bbf, 1)
-            dg1 = ops.make_conv(s_dh1, one.c(1), B, (1, 1, 1), eng.packed_bwd["2"], self.dfeat, npass=bnp)
+            bw.append(split_op(self.dh2, self.dh2_pl, B, hd, None, None, False))
+            s_dh2 = self.dh2_pl.src(0, hd, 1, 1, 1)
+            s_dh1 = self.dh1_pl.src(0, fs, 1, 1, 1)
+            wg2 = L.Wgrad(s_h1, one.c(0), s_dh2, B, 1, 1, 1, hd, fs, L.dptr(st.view("4.weight", grad=True)), bnp, 1, fbf, 1)
+            dg2 = ops.make_conv(s_dh2, 1, one.c(1), B, (1, 1, 1), eng.packed_bwd["4"], self.dh1, npass=bnp)
+            wg1 = L.Wgrad(s_feat, one.c(0), s_dh1, B, 1, 1, 1, fs, fs, L.dptr(st.view("2.weight", grad=True)), bnp, 1, fbf, 1)
+            dg1 = ops.make_conv(s_dh1, 1, one.c(1), B, (1, 1, 1), eng.packed_bwd["2"], self.dfeat, npass=bnp)
             self.keep += [s_dh2, wg2, dg2, s_dh1, wg1, dg1]
             bw.append((lib.coclr_conv_wgrad, (C.byref(wg2),)))
             bw.append((lib.coclr_conv_igemm, (C.byref(dg2), nsm)))
             bw.append((lib.coclr_bias_relu_bwd, (L.dptr(self.h1), L.dptr(b2), L.dptr(self.dh1),
                                                  L.dptr(st.view("2.bias", grad=True)), B, fs)))
+            bw.append(split_op(self.dh1, self.dh1_pl, B, fs, None, None, False))
             bw.append((lib.coclr_conv_wgrad, (C.byref(wg1),)))
             bw.append((lib.coclr_conv_igemm, (C.byref(dg1), nsm)))
             bw.append((lib.coclr_avgpool_bwd, (L.dptr(self.dfeat), L.dptr(out.grad), out.spec.C, 0, B, Pn, fs)))
             out.grad_written = True
-        # tensors in reverse creation order; each pushes gradient into its producers' sources
         convs_into, pool_into = {}, {}
         for kind, it in g.items:
             if kind == "conv":
@@ -411,27 +429,25 @@ class Plan:
                 boff_b = st.offsets[first + ".bias"][0]
                 bb = L.BnBwd(L.dptr(a.data), L.dptr(a.grad), t.C, 0, t.C, a.M, L.dptr(a.scale), L.dptr(a.shift),
                              L.dptr(a.mean), L.dptr(a.rstd), t.relu, L.dptr(a.bsums),
-                             L.dptr(st.grad[goff:]), L.dptr(st.grad[boff_b:]))
+                             L.dptr(st.grad[goff:]), L.dptr(st.grad[boff_b:]), L.dptr(a.dy.hi), L.dptr(a.dy.lo))
                 self.keep.append(bb)
                 bw.append((lib.coclr_bn_bwd, (C.byref(bb), nsm)))
                 for it in convs_into[t.index]:
                     sa = acts[it.src.index]
                     geom = ops.Geometry(it.k, it.s, it.p)
-                    cin_p = it.src.C
-                    dy = ops.make_src(a.grad, it.dst_coff, _round4(it.cout), a.dims[0], a.dims[1], a.dims[2])
-                    taps = geom.taps
-                    # pixel splits so that the grid roughly fills the device
-                    kreal = taps * cin_p
-                    bnk = min(256, ((kreal + ((kreal + 255) // 256) - 1) // ((kreal + 255) // 256) + 63) // 64 * 64)
+                    dy = a.dy.src(it.dst_coff, _round8(it.cout), a.dims[0], a.dims[1], a.dims[2])
+                    kreal = geom.taps * it.src.C
+                    kt = (kreal + 255) // 256
+                    bnk = (((kreal + kt - 1) // kt) + 63) // 64 * 64
                     tiles = ((kreal + bnk - 1) // bnk) * ((it.cout + 127) // 128)
                     chunks = (a.M + 63) // 64
                     splits = max(1, min(chunks, (2 * nsm + tiles - 1) // tiles))
                     wg = L.Wgrad(src_of(sa), geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin,
-                                 L.dptr(st.view(it.name + ".weight", grad=True)), bnp, bbf, splits)
+                                 L.dptr(st.view(it.name + ".weight", grad=True)), bnp, 1, fbf, splits)
                     self.keep += [wg, dy]
                     bw.append((lib.coclr_conv_wgrad, (C.byref(wg),)))
                     if it.need_dgrad:
-                        dg = ops.make_conv(dy, geom.c(1), B, sa.dims, eng.packed_bwd[it.name], sa.grad, 0,
+                        dg = ops.make_conv(dy, 1, geom.c(1), B, sa.dims, eng.packed_bwd[it.name], sa.grad, 0,
                                            accumulate=sa.grad_written, npass=bnp)
                         self.keep.append(dg)
                         bw.append((lib.coclr_conv_igemm, (C.byref(dg), nsm)))
@@ -440,8 +456,7 @@ class Plan:
                 it = pool_into[t.index]
                 sa = acts[it.src.index]
                 geom = ops.Geometry(it.k, it.s, it.p)
-                pl = L.Pool(L.dptr(sa.data), it.src.C, 0, None, None, 0,
-                            L.dptr(a.data), t.C, 0, L.dptr(a.idx), B, t.C,
+                pl = L.Pool(None, None, it.src.C, 0, None, None, t.C, 0, L.dptr(a.idx), B, t.C,
                             sa.dims[0], sa.dims[1], sa.dims[2], a.dims[0], a.dims[1], a.dims[2], geom.c(0),
                             L.dptr(a.grad), L.dptr(sa.grad), int(sa.grad_written))
                 self.keep.append(pl)
@@ -452,13 +467,15 @@ class Plan:
 class EncoderEngine:
     """Executes one encoder (see module docstring)."""
 
+    profile = None  # set to a list to collect (fn name, args, start event, end event) per launch (bench / tuning only)
+
     def __init__(self, store, graph, precision="parity"):
         if precision not in PRECISIONS:
             raise ValueError("precision must be one of %s" % list(PRECISIONS))
         self.store, self.graph, self.precision = store, graph, precision
         self.plans = {}
         dev = store.device
-        fnp, fbf, bnp, bbf = PRECISIONS[precision]
+        fnp, fbf, bnp = PRECISIONS[precision]
         self.packed_fwd, self.packed_bwd, self._packs = {}, {}, []
         for kind, it in graph.items:
             if kind != "conv":
@@ -469,7 +486,7 @@ class EncoderEngine:
             self.packed_fwd[it.name] = pf
             self._packs.append((pf, w, False))
             if it.need_dgrad:
-                pb = ops.PackedWeights(it.cout, it.cin, taps, _round4(it.cout), 1, bbf, dev)
+                pb = ops.PackedWeights(it.cout, it.cin, taps, _round8(it.cout), 1, 1, dev)
                 self.packed_bwd[it.name] = pb
                 self._packs.append((pb, w, True))
         if graph.head_dim is not None:
@@ -477,7 +494,7 @@ class EncoderEngine:
             for nm, co in (("2", fs), ("4", hd)):
                 w = store.view(nm + ".weight")
                 pf = ops.PackedWeights(co, fs, 1, fs, 0, fbf, dev)
-                pb = ops.PackedWeights(co, fs, 1, _round4(co), 1, bbf, dev)
+                pb = ops.PackedWeights(co, fs, 1, _round8(co), 1, 1, dev)
                 self.packed_fwd[nm], self.packed_bwd[nm] = pf, pb
                 self._packs += [(pf, w, False), (pb, w, True)]
 
@@ -495,8 +512,6 @@ class EncoderEngine:
             p = Plan(self, B, T, H, W, training, with_backward)
             self.plans[key] = p
         return p
-
-    profile = None  # set to a list to collect (fn name, start event, end event) per launch (bench / tuning only)
 
     def _run(self, oplist):
         stream = L.stream_ptr()
@@ -516,7 +531,7 @@ class EncoderEngine:
     def forward(self, x, training=True, with_backward=False, repack=True, batch_index=None, batch=None):
         """x: [*, C, T, H, W] fp32 CUDA (any batch stride). Clip b of the pass is x[batch_index[b]] when a
         device int64 index is given (shuffle-BN gather), else x[b].  Returns the plan; plan.q holds the
-        normalised features [B, dim] (plan.backbone_out the raw backbone output when there is no head)."""
+        normalised features [B, dim] (plan.backbone_out the backbone output when there is no head)."""
         if not x.is_cuda:
             raise L.CoclrError("coclr_b200 encoders run on CUDA only (no CPU fallback)")
         _, Cin, T, H, W = x.shape
@@ -532,8 +547,9 @@ class EncoderEngine:
             p.stats.zero_()
             self.store.nbt += 1
         lib = L.load()
-        L.check(lib.coclr_pack_input(L.dptr(x), x.stride(0), x.stride(1), Cin, L.dptr(p.input.data), B, T * H * W,
-                                     L.dptr(batch_index), L.stream_ptr()), "coclr_pack_input")
+        L.check(lib.coclr_pack_input(L.dptr(x), x.stride(0), x.stride(1), Cin, L.dptr(p.input.pl.hi),
+                                     L.dptr(p.input.pl.lo), B, T * H * W, L.dptr(batch_index), L.stream_ptr()),
+                "coclr_pack_input")
         self._run(p.fwd)
         return p
 
@@ -543,6 +559,4 @@ class EncoderEngine:
         self._run(p.bwd)
 
     def backbone_output_ncdhw(self, p):
-        a = p.backbone_out
-        y = torch.relu(a.data * a.scale + a.shift)
-        return y.permute(0, 4, 1, 2, 3).contiguous()
+        return p.backbone_out.pl.value().permute(0, 4, 1, 2, 3).contiguous()

@@ -18,9 +18,8 @@ class CoclrError(RuntimeError):
 
 
 class Src(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("ld", C.c_int), ("coff", C.c_int), ("C", C.c_int),
-                ("T", C.c_int), ("H", C.c_int), ("W", C.c_int),
-                ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int)]
+    _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("ld", C.c_int), ("coff", C.c_int), ("C", C.c_int),
+                ("T", C.c_int), ("H", C.c_int), ("W", C.c_int)]
 
 
 class Geom(C.Structure):
@@ -37,20 +36,27 @@ class Conv(C.Structure):
                 ("N", C.c_int), ("BN", C.c_int), ("n_tiles", C.c_int),
                 ("dst", C.c_void_p), ("dst_ld", C.c_int), ("dst_coff", C.c_int),
                 ("accumulate", C.c_int), ("stats_sum", C.c_void_p), ("stats_sq", C.c_void_p),
-                ("npass", C.c_int), ("bf16", C.c_int)]
+                ("npass", C.c_int), ("a_bf16", C.c_int), ("b_bf16", C.c_int)]
 
 
 class Wgrad(C.Structure):
     _fields_ = [("src", Src), ("g", Geom), ("dy", Src),
                 ("B", C.c_int), ("Td", C.c_int), ("Hd", C.c_int), ("Wd", C.c_int),
                 ("Cout", C.c_int), ("Cin_real", C.c_int), ("dw", C.c_void_p),
-                ("npass", C.c_int), ("bf16", C.c_int), ("splits", C.c_int)]
+                ("npass", C.c_int), ("dy_bf16", C.c_int), ("src_bf16", C.c_int), ("splits", C.c_int)]
 
 
 class Pack(C.Structure):
     _fields_ = [("w", C.c_void_p), ("Cout", C.c_int), ("Cin", C.c_int), ("taps", C.c_int),
                 ("Cpad", C.c_int), ("mode", C.c_int), ("bf16", C.c_int),
                 ("wpk", C.c_void_p), ("unscale", C.c_void_p)]
+
+
+class Split(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("ld", C.c_int), ("coff", C.c_int), ("C", C.c_int), ("M", C.c_long),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int),
+                ("hi", C.c_void_p), ("lo", C.c_void_p), ("out_ld", C.c_int), ("out_coff", C.c_int),
+                ("bf16", C.c_int)]
 
 
 class BnFinalize(C.Structure):
@@ -66,13 +72,14 @@ class BnBwd(C.Structure):
     _fields_ = [("y", C.c_void_p), ("dA", C.c_void_p), ("ld", C.c_int), ("coff", C.c_int), ("C", C.c_int),
                 ("M", C.c_long), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("mean", C.c_void_p), ("rstd", C.c_void_p), ("relu", C.c_int),
-                ("sums", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p)]
+                ("sums", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+                ("dy_hi", C.c_void_p), ("dy_lo", C.c_void_p)]
 
 
 class Pool(C.Structure):
-    _fields_ = [("x", C.c_void_p), ("ldx", C.c_int), ("x_coff", C.c_int),
-                ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int),
-                ("y", C.c_void_p), ("ldy", C.c_int), ("y_coff", C.c_int), ("idx", C.c_void_p),
+    _fields_ = [("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("ldx", C.c_int), ("x_coff", C.c_int),
+                ("y_hi", C.c_void_p), ("y_lo", C.c_void_p), ("ldy", C.c_int), ("y_coff", C.c_int),
+                ("idx", C.c_void_p),
                 ("B", C.c_int), ("C", C.c_int), ("Ti", C.c_int), ("Hi", C.c_int), ("Wi", C.c_int),
                 ("To", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int), ("g", Geom),
                 ("dy", C.c_void_p), ("dx", C.c_void_p), ("accumulate", C.c_int)]

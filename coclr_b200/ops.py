@@ -1,5 +1,5 @@
 """Thin Python wrappers (torch tensors -> raw pointers) over the C ABI. No autograd here; the
-encoder-level autograd.Function lives in engine.py."""
+encoder-level autograd.Function lives in moco.py / engine.py."""
 import ctypes as C
 
 import torch
@@ -8,7 +8,7 @@ from . import lib as L
 
 
 class Geometry:
-    """Conv geometry (kernel, stride, padding) per (t, h, w)."""
+    """Conv / pool geometry (kernel, stride, padding) per (t, h, w)."""
 
     def __init__(self, k, s=(1, 1, 1), p=(0, 0, 0)):
         self.k, self.s, self.p = tuple(k), tuple(s), tuple(p)
@@ -25,10 +25,35 @@ class Geometry:
                       self.p[0], self.p[1], self.p[2], int(transposed))
 
 
-def make_src(x, coff, Cc, T, H, W, scale=None, shift=None, relu=False):
-    """x: fp32 CUDA tensor whose last dim is the per-pixel channel stride (channels-last rows)."""
-    assert x.dtype == torch.float32 and x.is_contiguous()
-    return L.Src(L.dptr(x), x.shape[-1], coff, Cc, T, H, W, L.dptr(scale), L.dptr(shift), int(bool(relu)))
+class Planes:
+    """A split-precision channels-last activation: two 16-bit planes [B,T,H,W,C] with hi + lo ~= value."""
+
+    def __init__(self, shape, bf16, device, lo=True):
+        dt = torch.bfloat16 if bf16 else torch.float16
+        self.bf16 = int(bool(bf16))
+        self.hi = torch.empty(shape, dtype=dt, device=device)
+        self.lo = torch.empty(shape, dtype=dt, device=device) if lo else None
+
+    @property
+    def ld(self):
+        return self.hi.shape[-1]
+
+    def value(self):
+        v = self.hi.float()
+        return v + self.lo.float() if self.lo is not None else v
+
+    def src(self, coff, Cc, T, H, W):
+        return L.Src(L.dptr(self.hi), L.dptr(self.lo), self.ld, coff, Cc, T, H, W)
+
+
+def split_into(x, planes, coff=0, Cc=None, scale=None, shift=None, relu=False, out_coff=0):
+    """planes[..., out_coff:out_coff+C] = split(relu?(scale*x[..., coff:coff+C]+shift)); x fp32 rows."""
+    Cc = Cc or x.shape[-1]
+    M = x.numel() // x.shape[-1]
+    p = L.Split(L.dptr(x), x.shape[-1], coff, Cc, M, L.dptr(scale), L.dptr(shift), int(bool(relu)),
+                L.dptr(planes.hi), L.dptr(planes.lo), planes.ld, out_coff, planes.bf16)
+    L.check(L.load().coclr_affine_split(C.byref(p), L.num_sms(), L.stream_ptr()), "coclr_affine_split")
+    return planes
 
 
 def packed_layout(N, Kreal):
@@ -58,22 +83,24 @@ class PackedWeights:
         return self
 
 
-def make_conv(src, geom_c, B, dst_dims, pw, dst, dst_coff=0, accumulate=False, stats_sum=None, stats_sq=None, npass=3):
+def make_conv(src, a_bf16, geom_c, B, dst_dims, pw, dst, dst_coff=0, accumulate=False, stats_sum=None,
+              stats_sq=None, npass=3):
     Td, Hd, Wd = dst_dims
     return L.Conv(src, geom_c, B, Td, Hd, Wd, pw.Kreal, L.dptr(pw.wpk), L.dptr(pw.unscale),
                   pw.N, pw.BN, pw.n_tiles, L.dptr(dst), dst.shape[-1], dst_coff, int(bool(accumulate)),
-                  L.dptr(stats_sum), L.dptr(stats_sq), npass, pw.bf16)
+                  L.dptr(stats_sum), L.dptr(stats_sq), npass, int(a_bf16), pw.bf16)
 
 
-def conv_igemm(src, geom_c, B, dst_dims, pw, dst, dst_coff=0, accumulate=False, stats=None, npass=3):
-    """Run the implicit-GEMM conv. src: L.Src; geom_c: L.Geom; dst: [B,Td,Hd,Wd,ld] fp32."""
+def conv_igemm(src, a_bf16, geom_c, B, dst_dims, pw, dst, dst_coff=0, accumulate=False, stats=None, npass=3):
+    """Run the implicit-GEMM conv. src: L.Src of 16-bit planes; dst: [B,Td,Hd,Wd,ld] fp32."""
     ssum = stats[:pw.N] if stats is not None else None
     ssq = stats[pw.N:] if stats is not None else None
-    p = make_conv(src, geom_c, B, dst_dims, pw, dst, dst_coff, accumulate, ssum, ssq, npass)
+    p = make_conv(src, a_bf16, geom_c, B, dst_dims, pw, dst, dst_coff, accumulate, ssum, ssq, npass)
     L.check(L.load().coclr_conv_igemm(C.byref(p), L.num_sms(), L.stream_ptr()), "coclr_conv_igemm")
 
 
-def conv_wgrad(src, geom_c, dy_src, B, dst_dims, Cout, Cin_real, dw, npass=3, bf16=True, splits=1):
+def conv_wgrad(src, src_bf16, geom_c, dy_src, dy_bf16, B, dst_dims, Cout, Cin_real, dw, npass=3, splits=1):
     Td, Hd, Wd = dst_dims
-    p = L.Wgrad(src, geom_c, dy_src, B, Td, Hd, Wd, Cout, Cin_real, L.dptr(dw), npass, int(bool(bf16)), splits)
+    p = L.Wgrad(src, geom_c, dy_src, B, Td, Hd, Wd, Cout, Cin_real, L.dptr(dw), npass, int(dy_bf16), int(src_bf16),
+                splits)
     L.check(L.load().coclr_conv_wgrad(C.byref(p), L.stream_ptr()), "coclr_conv_wgrad")

@@ -5,7 +5,13 @@
  * nn.BatchNorm3d / nn.MaxPool3d / torch.einsum.  Each entry point below
  * replaces the vendor-library call(s) named in its comment (reference file:line), takes raw device
  * pointers + sizes + a cudaStream_t, never allocates, never synchronises, and returns 0 on success
- * or a negative error code (COCLR_E_*).  All activations are channels-last (N,D,H,W,C) fp32 rows.
+ * or a negative error code (COCLR_E_*).
+ *
+ * Data layout: activations are channels-last rows [B, T, H, W, ld].  A convolution OUTPUT is written as
+ * fp32 (pre-BatchNorm, needed for the statistics and the backward pass); every convolution INPUT is a
+ * pair of 16-bit planes (hi, lo) of the same shape with hi + lo ~= the fp32 value (fp16 pair: ~22 bits,
+ * bf16 pair: ~16 bits), produced by coclr_affine_split / coclr_maxpool_fwd / coclr_pack_input /
+ * coclr_bn_bwd.  Three tensor-core passes (hi*lo, lo*hi, hi*hi) then give an fp32-grade product.
  *
  * The Python host side (coclr_b200/lib.py) binds these with ctypes; INTEGRATION.md shows the stub.
  */
@@ -26,18 +32,14 @@ extern "C" {
 
 typedef void* coclr_stream_t; /* cudaStream_t */
 
-/* A channels-last fp32 activation as an implicit-GEMM operand source.  The value used is
- *   relu?( scale[c] * x + shift[c] )   (BatchNorm-apply + ReLU folded into the operand load),
- * or x itself when scale == NULL. */
+/* A channels-last split-precision activation as an implicit-GEMM operand source. */
 typedef struct {
-  const float* ptr;   /* [B, T, H, W, ld] */
-  int ld;             /* channels per pixel in memory */
-  int coff;           /* first channel used */
-  int C;              /* channels used (multiple of 4) */
+  const void* hi; /* 16-bit plane [B, T, H, W, ld] (fp16 or bf16), 16-byte aligned */
+  const void* lo; /* residual plane, same layout; may be NULL for single-pass kernels */
+  int ld;         /* channels per pixel in memory (multiple of 8) */
+  int coff;       /* first channel used (multiple of 8) */
+  int C;          /* channels used (multiple of 8) */
   int T, H, W;
-  const float* scale; /* [C] or NULL */
-  const float* shift; /* [C] or NULL */
-  int relu;
 } coclr_src_t;
 
 typedef struct {
@@ -60,13 +62,14 @@ typedef struct {
   const void* wpk;   /* packed weights from coclr_pack_weights */
   const float* wunscale; /* [n_tiles*BN] per-column 1/scale, or NULL */
   int N, BN, n_tiles;    /* real output channels, tile width (multiple of 32, <= 256), tiles */
-  float* dst;
+  float* dst;            /* fp32 [B,Td,Hd,Wd,dst_ld] */
   int dst_ld, dst_coff;
-  int accumulate;  /* dst += result */
+  int accumulate;    /* dst += result */
   double* stats_sum; /* [N] per-output-channel sum of Y, accumulated (zero it first); NULL to skip */
   double* stats_sq;  /* [N] per-output-channel sum of Y*Y */
-  int npass;       /* 1 = single 16-bit pass, 3 = hi/lo split (fp32-equivalent) */
-  int bf16;        /* 0 = fp16 operands, 1 = bf16 operands */
+  int npass;         /* 1 = single 16-bit pass, 3 = hi/lo split (fp32-grade) */
+  int a_bf16;        /* format of the src planes: 0 = fp16, 1 = bf16 */
+  int b_bf16;        /* format of the packed weights */
 } coclr_conv_t;
 int coclr_conv_igemm(const coclr_conv_t* p, int num_sms, coclr_stream_t stream);
 size_t coclr_conv_packed_bytes(int N, int Kreal, int* BN_out, int* n_tiles_out);
@@ -75,13 +78,14 @@ size_t coclr_conv_packed_bytes(int N, int Kreal, int* BN_out, int* n_tiles_out);
  * replaces cuDNN wgrad.  dW[n, c, tap] += sum_m dY[m, n] * A[m, (tap, c)] into the PyTorch weight
  * layout [Cout, Cin_real, kt, kh, kw] (fp32 atomics; zero dW first). */
 typedef struct {
-  coclr_src_t src;   /* conv input (forward operand, affine+relu folded) */
+  coclr_src_t src;   /* conv input planes (as the forward pass consumed them) */
   coclr_geom_t g;    /* forward geometry (transposed = 0) */
-  coclr_src_t dy;    /* output gradient [B,Td,Hd,Wd,ld], C = Cout rounded up to 4; scale = NULL */
+  coclr_src_t dy;    /* output-gradient planes [B,Td,Hd,Wd,ld], C = Cout rounded up to 8 */
   int B, Td, Hd, Wd;
-  int Cout, Cin_real; /* real sizes of dW (src.C may be padded, e.g. 4 for the RGB stem) */
+  int Cout, Cin_real; /* real sizes of dW (src.C may be padded, e.g. 8 for the RGB stem) */
   float* dw;
-  int npass, bf16;
+  int npass;
+  int dy_bf16, src_bf16;
   int splits;        /* pixel-range splits (>= 1) */
 } coclr_wgrad_t;
 int coclr_conv_wgrad(const coclr_wgrad_t* p, coclr_stream_t stream);
@@ -101,9 +105,27 @@ typedef struct {
 } coclr_pack_t;
 int coclr_pack_weights(const coclr_pack_t* p, coclr_stream_t stream);
 
-/* ---- BatchNorm3d (train mode; backbone/s3dg.py:16,46-47) ------------------------------------------
- * finalize: per-channel sums written by coclr_conv_igemm -> (scale, shift) consumed by the next
- * operand load, saved (mean, rstd) for backward, running-stat momentum update (unbiased variance).
+/* ---- BatchNorm-apply + ReLU + precision split --------------------------------------------------
+ * hi/lo[m, out_coff + c] = split( relu?( scale[c] * x[m, coff + c] + shift[c] ) ); scale == NULL: identity.
+ * The elementwise half of nn.BatchNorm3d + nn.ReLU (backbone/s3dg.py:16-17,24-27), one pass, producing the
+ * operand planes every consumer (conv / pool / avg-pool) reads. */
+typedef struct {
+  const float* x;
+  int ld, coff, C; /* C multiple of 4 */
+  long M;
+  const float* scale;
+  const float* shift;
+  int relu;
+  void* hi;
+  void* lo; /* may be NULL */
+  int out_ld, out_coff;
+  int bf16;
+} coclr_split_t;
+int coclr_affine_split(const coclr_split_t* p, int num_sms, coclr_stream_t stream);
+
+/* ---- BatchNorm3d statistics -> affine (train mode; backbone/s3dg.py:16,46-47) ------------------
+ * per-channel sums written by coclr_conv_igemm -> (scale, shift) for coclr_affine_split, saved (mean, rstd)
+ * for backward, running-stat momentum update (unbiased variance).
  * training == 0: scale/shift from the running statistics (eval-mode BN, main_coclr.py:363). */
 typedef struct {
   const double* sum;
@@ -123,11 +145,12 @@ typedef struct {
 } coclr_bn_finalize_t;
 int coclr_bn_finalize(const coclr_bn_finalize_t* p, coclr_stream_t stream);
 
-/* backward of BatchNorm+ReLU, in place: dA (grad w.r.t. relu(bn(y))) -> dY (grad w.r.t. y);
- * also dgamma / dbeta.  Replaces NativeBatchNormBackward0 + ReluBackward0. */
+/* backward of BatchNorm+ReLU: dA (grad w.r.t. relu(bn(y)), fp32) -> dY (grad w.r.t. y) written as bf16
+ * hi/lo planes for the dgrad / wgrad kernels; also dgamma / dbeta (accumulated).  Replaces
+ * NativeBatchNormBackward0 + ReluBackward0. */
 typedef struct {
-  const float* y; /* raw conv output [M, ld] */
-  float* dA;      /* same layout, overwritten with dY */
+  const float* y;  /* raw conv output [M, ld] */
+  const float* dA; /* same layout */
   int ld, coff, C;
   long M;
   const float* scale; /* [C] gamma*rstd (as written by finalize) */
@@ -136,45 +159,46 @@ typedef struct {
   const float* rstd;
   int relu;
   double* sums;   /* workspace [2*C] */
-  float* dgamma;  /* [C] or NULL */
+  float* dgamma;  /* [C] or NULL, += */
   float* dbeta;
+  void* dy_hi;    /* bf16 planes [M, ld] (same ld / coff as y) */
+  void* dy_lo;    /* may be NULL */
 } coclr_bn_bwd_t;
 int coclr_bn_bwd(const coclr_bn_bwd_t* p, int num_sms, coclr_stream_t stream);
 
-/* bias+ReLU backward of the projection head (model/pretrain.py:52-53) */
+/* bias+ReLU backward of the projection head (model/pretrain.py:52-53): dA <- dA*[h+b>0] in place, dbias += */
 int coclr_bias_relu_bwd(const float* h, const float* bias, float* dA, float* dbias, int M, int C,
                         coclr_stream_t stream);
 
 /* ---- nn.MaxPool3d (backbone/s3dg.py:105,151,162,173,190) ---------------------------------------- */
 typedef struct {
-  const float* x; /* input [B,Ti,Hi,Wi,ldx] */
+  const void* x_hi; /* input planes [B,Ti,Hi,Wi,ldx] fp16 */
+  const void* x_lo;
   int ldx, x_coff;
-  const float* scale; /* pending affine of the input (NULL: none) */
-  const float* shift;
-  int relu;
-  float* y; /* output [B,To,Ho,Wo,ldy] (final values) */
+  void* y_hi;       /* output planes [B,To,Ho,Wo,ldy] fp16 */
+  void* y_lo;
   int ldy, y_coff;
-  unsigned char* idx; /* [B*To*Ho*Wo, C] arg-max tap */
+  unsigned char* idx; /* [B*To*Ho*Wo, C] arg-max tap, may be NULL in forward-only use */
   int B, C, Ti, Hi, Wi, To, Ho, Wo;
   coclr_geom_t g;
-  /* backward only */
-  const float* dy;
-  float* dx;
+  /* backward only: fp32 gradient buffers */
+  const float* dy; /* [B,To,Ho,Wo,C] */
+  float* dx;       /* [B,Ti,Hi,Wi,ldx] at x_coff */
   int accumulate;
 } coclr_pool_t;
 int coclr_maxpool_fwd(const coclr_pool_t* p, coclr_stream_t stream);
 int coclr_maxpool_bwd(const coclr_pool_t* p, coclr_stream_t stream);
 
 /* ---- nn.AdaptiveAvgPool3d((1,1,1)) (model/pretrain.py:51) ---------------------------------------- */
-int coclr_avgpool_fwd(const float* x, int ld, int coff, const float* scale, const float* shift, int relu,
-                      float* out, int B, int Pn, int C, coclr_stream_t stream);
+int coclr_avgpool_fwd(const void* x_hi, const void* x_lo, int ld, int coff, float* out, int B, int Pn, int C,
+                      coclr_stream_t stream);
 int coclr_avgpool_bwd(const float* dfeat, float* dA, int ld, int coff, int B, int Pn, int C, coclr_stream_t stream);
 
-/* ---- block[:, i].contiguous() + NCDHW->NDHW4 (model/pretrain.py:149-150); batch_index (device int64[B],
- * or NULL) gathers source clips out[b] = x[batch_index[b]] = the shuffle-BN pick x_gather[idx_this]
- * (pretrain.py:124) without a separate copy ------------------------------------------------------- */
-int coclr_pack_input(const float* x, long batch_stride, long chan_stride, int Cin, float* out, int B, long thw,
-                     const long* batch_index, coclr_stream_t stream);
+/* ---- block[:, i].contiguous() + NCDHW -> channels-last fp16 hi/lo planes with C padded to 8
+ * (model/pretrain.py:149-150); batch_index (device int64[B], or NULL) gathers source clips
+ * out[b] = x[batch_index[b]] = the shuffle-BN pick x_gather[idx_this] (pretrain.py:124) ------------ */
+int coclr_pack_input(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi, void* out_lo, int B,
+                     long thw, const long* batch_index, coclr_stream_t stream);
 
 /* ---- F.normalize(z + bias, dim=1) (model/pretrain.py:154,167) ------------------------------------- */
 int coclr_l2norm_fwd(const float* z, const float* bias, float* q, float* inv_norm, int B, int D, coclr_stream_t stream);

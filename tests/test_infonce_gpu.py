@@ -140,7 +140,7 @@ def test_layerwise_activations(step, diag):
         if not t.pending:
             continue
         a = plan.acts[t.index]
-        y = torch.relu(a.data * a.scale + a.shift)
+        y = a.pl.value()          # relu(bn(conv)) as the consumers read it (fp16 hi + lo planes)
         for nm, coff, c in t.bn_members:
             ref = rec["encoder_q." + nm].permute(0, 2, 3, 4, 1)
             e = _rel_l2(y[..., coff:coff + c], ref)
