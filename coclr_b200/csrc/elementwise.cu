@@ -102,6 +102,9 @@ __global__ void __launch_bounds__(256) affine_split_kernel(const coclr_split_t P
       v.w = fmaxf(v.w, 0.f);
     }
     st_pair4<kBf16>(hi, lo, (size_t)(r * P.out_ld + P.out_coff + c), v);
+    if (P.hi2 != nullptr)
+      st_pair4<true>(reinterpret_cast<uint16_t*>(P.hi2), reinterpret_cast<uint16_t*>(P.lo2),
+                     (size_t)(r * P.out_ld + P.out_coff + c), v);
   }
 }
 
@@ -286,6 +289,9 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const coclr_pool_t P) 
     if (yl != nullptr)
       *reinterpret_cast<uint2*>(yl + oo) =
           make_uint2((uint32_t)bl[0] | ((uint32_t)bl[1] << 16), (uint32_t)bl[2] | ((uint32_t)bl[3] << 16));
+    if (P.y2_hi != nullptr)
+      st_pair4<true>(reinterpret_cast<uint16_t*>(P.y2_hi), reinterpret_cast<uint16_t*>(P.y2_lo), oo,
+                     make_float4(best[0], best[1], best[2], best[3]));
     if (P.idx) *reinterpret_cast<uchar4*>(P.idx + o * P.C + c) = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
   }
 }
@@ -382,7 +388,8 @@ __global__ void avgpool_bwd_kernel(const float* dfeat, float* dA, int ld, int co
 // .contiguous() copies, model/pretrain.py:149-150, are folded in) -> fp16 hi/lo planes [b, thw, 8]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_input_kernel(const float* x, long batch_stride, long chan_stride, int Cin,
-                                                         uint16_t* out_hi, uint16_t* out_lo, int B, long thw,
+                                                         uint16_t* out_hi, uint16_t* out_lo, uint16_t* out2_hi,
+                                                         uint16_t* out2_lo, int B, long thw,
                                                          const long* __restrict__ batch_index) {
   const long total = (long)B * thw;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -390,10 +397,15 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* x, long ba
     const long sb = batch_index ? batch_index[b] : b;  // shuffle-BN gather folded in (pretrain.py:124)
     const float* s = x + sb * batch_stride + p;
     uint16_t h[8], l[8];
+    float vv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float v = j < Cin ? s[(long)j * chan_stride] : 0.f;
-      split2<false>(v, h[j], l[j]);
+      vv[j] = j < Cin ? s[(long)j * chan_stride] : 0.f;
+      split2<false>(vv[j], h[j], l[j]);
+    }
+    if (out2_hi != nullptr) {
+      st_pair4<true>(out2_hi, out2_lo, (size_t)i * 8, make_float4(vv[0], vv[1], vv[2], vv[3]));
+      st_pair4<true>(out2_hi, out2_lo, (size_t)i * 8 + 4, make_float4(vv[4], vv[5], vv[6], vv[7]));
     }
     *reinterpret_cast<uint4*>(out_hi + i * 8) =
         make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
@@ -595,11 +607,12 @@ extern "C" int coclr_avgpool_bwd(const float* dfeat, float* dA, int ld, int coff
 }
 
 extern "C" int coclr_pack_input(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi, void* out_lo,
-                                int B, long thw, const long* batch_index, coclr_stream_t stream) {
+                                void* out2_hi, void* out2_lo, int B, long thw, const long* batch_index,
+                                coclr_stream_t stream) {
   if (!x || !out_hi || Cin < 1 || Cin > 8) return COCLR_E_ARG;
   pack_input_kernel<<<grid_for((long)B * thw, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
-      x, batch_stride, chan_stride, Cin, reinterpret_cast<uint16_t*>(out_hi), reinterpret_cast<uint16_t*>(out_lo), B, thw,
-      batch_index);
+      x, batch_stride, chan_stride, Cin, reinterpret_cast<uint16_t*>(out_hi), reinterpret_cast<uint16_t*>(out_lo),
+      reinterpret_cast<uint16_t*>(out2_hi), reinterpret_cast<uint16_t*>(out2_lo), B, thw, batch_index);
   return LAUNCH_OK();
 }
 

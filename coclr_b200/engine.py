@@ -254,7 +254,7 @@ class ParamStore:
 # shape-specific plan
 # ---------------------------------------------------------------------------------------------
 class _Act:
-    __slots__ = ("spec", "dims", "data", "pl", "grad", "dy", "scale", "shift", "mean", "rstd", "ssum", "ssq", "idx",
+    __slots__ = ("spec", "dims", "data", "pl", "plw", "grad", "dy", "scale", "shift", "mean", "rstd", "ssum", "ssq", "idx",
                  "bsums", "grad_written", "M")
 
 
@@ -269,7 +269,6 @@ class Plan:
         self.fwd, self.bwd = [], []
         nsm = L.num_sms(dev)
         fnp, fbf, bnp = PRECISIONS[eng.precision]
-        need_lo = fnp > 1 or (with_backward and bnp > 1)
         # ---- activations ----
         acts = {}
         n_stat = sum(t.C for t in g.tensors if t.pending)
@@ -281,7 +280,10 @@ class Plan:
             a.spec, a.dims = t, t.dims_fn((T, H, W))
             a.M = B * a.dims[0] * a.dims[1] * a.dims[2]
             shape = (B,) + a.dims + (t.C,)
-            a.pl = ops.Planes(shape, fbf, dev, lo=need_lo)          # what every consumer reads
+            a.pl = ops.Planes(shape, fbf, dev, lo=fnp > 1)          # what every forward consumer reads
+            # bf16 twin for the weight-gradient GEMM (tcgen05 kind::f16 needs one format for both operands and
+            # the output gradients are bf16); not needed when the forward planes already are bf16
+            a.plw = ops.Planes(shape, 1, dev, lo=bnp > 1) if (with_backward and not fbf) else (a.pl if with_backward else None)
             a.data = a.grad = a.dy = a.idx = a.bsums = None
             a.grad_written = False
             if t.pending:
@@ -307,9 +309,15 @@ class Plan:
         def src_of(a):
             return a.pl.src(0, a.spec.C, a.dims[0], a.dims[1], a.dims[2])
 
-        def split_op(x, planes, M, Cc, scale, shift, relu):
+        def twin_ptrs(pl, plw):
+            if plw is None or plw is pl:
+                return None, None
+            return L.dptr(plw.hi), L.dptr(plw.lo)
+
+        def split_op(x, planes, M, Cc, scale, shift, relu, twin=None):
+            t_hi, t_lo = twin_ptrs(planes, twin)
             sp = L.Split(L.dptr(x), x.shape[-1], 0, Cc, M, L.dptr(scale), L.dptr(shift), int(bool(relu)),
-                         L.dptr(planes.hi), L.dptr(planes.lo), planes.ld, 0, planes.bf16)
+                         L.dptr(planes.hi), L.dptr(planes.lo), planes.ld, 0, planes.bf16, t_hi, t_lo)
             self.keep.append(sp)
             return (lib.coclr_affine_split, (C.byref(sp), nsm))
 
@@ -329,8 +337,9 @@ class Plan:
                 geom = ops.Geometry(it.k, it.s, it.p)
                 if with_backward:
                     da.idx = torch.empty(da.M * it.dst.C, dtype=torch.uint8, device=dev)
+                t_hi, t_lo = twin_ptrs(da.pl, da.plw)
                 pl = L.Pool(L.dptr(sa.pl.hi), L.dptr(sa.pl.lo), it.src.C, 0, L.dptr(da.pl.hi), L.dptr(da.pl.lo),
-                            it.dst.C, 0, L.dptr(da.idx), B, it.dst.C,
+                            it.dst.C, 0, t_hi, t_lo, L.dptr(da.idx), B, it.dst.C,
                             sa.dims[0], sa.dims[1], sa.dims[2], da.dims[0], da.dims[1], da.dims[2], geom.c(0),
                             None, None, 0)
                 self.keep.append(pl)
@@ -348,7 +357,7 @@ class Plan:
                                   L.dptr(a.mean), L.dptr(a.rstd), it.C)
                 self.keep.append(bf)
                 self.fwd.append((lib.coclr_bn_finalize, (C.byref(bf),)))
-                self.fwd.append(split_op(a.data, a.pl, a.M, it.C, a.scale, a.shift, it.relu))
+                self.fwd.append(split_op(a.data, a.pl, a.M, it.C, a.scale, a.shift, it.relu, a.plw))
         # ---- head ----
         out = acts[g.backbone_out.index]
         self.backbone_out = out
@@ -362,11 +371,14 @@ class Plan:
             self.q = torch.empty(B, hd, **f32)
             self.inv_norm = torch.empty(B, **f32)
             self.ones = torch.ones(fs, **f32)
-            self.feat_pl = ops.Planes((B, 1, 1, 1, fs), fbf, dev, lo=need_lo)
-            self.h1_pl = ops.Planes((B, 1, 1, 1, fs), fbf, dev, lo=need_lo)
+            self.feat_pl = ops.Planes((B, 1, 1, 1, fs), fbf, dev, lo=fnp > 1)
+            self.h1_pl = ops.Planes((B, 1, 1, 1, fs), fbf, dev, lo=fnp > 1)
+            mk_twin = with_backward and not fbf
+            self.feat_plw = ops.Planes((B, 1, 1, 1, fs), 1, dev, lo=bnp > 1) if mk_twin else self.feat_pl
+            self.h1_plw = ops.Planes((B, 1, 1, 1, fs), 1, dev, lo=bnp > 1) if mk_twin else self.h1_pl
             self.fwd.append((lib.coclr_avgpool_fwd, (L.dptr(out.pl.hi), L.dptr(out.pl.lo), out.spec.C, 0,
                                                      L.dptr(self.feat), B, Pn, fs)))
-            self.fwd.append(split_op(self.feat, self.feat_pl, B, fs, None, None, False))
+            self.fwd.append(split_op(self.feat, self.feat_pl, B, fs, None, None, False, self.feat_plw))
             one = ops.Geometry((1, 1, 1))
             b2, b4 = st.view("2.bias"), st.view("4.bias")
             s_feat = self.feat_pl.src(0, fs, 1, 1, 1)
@@ -375,7 +387,7 @@ class Plan:
             c2 = ops.make_conv(s_h1, fbf, one.c(0), B, (1, 1, 1), eng.packed_fwd["4"], self.h2, npass=fnp)
             self.keep += [c1, c2, s_feat, s_h1]
             self.fwd.append((lib.coclr_conv_igemm, (C.byref(c1), nsm)))
-            self.fwd.append(split_op(self.h1, self.h1_pl, B, fs, self.ones, b2, True))   # bias + ReLU
+            self.fwd.append(split_op(self.h1, self.h1_pl, B, fs, self.ones, b2, True, self.h1_plw))   # bias + ReLU
             self.fwd.append((lib.coclr_conv_igemm, (C.byref(c2), nsm)))
             self.fwd.append((lib.coclr_l2norm_fwd, (L.dptr(self.h2), L.dptr(b4), L.dptr(self.q), L.dptr(self.inv_norm), B, hd)))
         if not with_backward:
@@ -394,9 +406,11 @@ class Plan:
             bw.append(split_op(self.dh2, self.dh2_pl, B, hd, None, None, False))
             s_dh2 = self.dh2_pl.src(0, hd, 1, 1, 1)
             s_dh1 = self.dh1_pl.src(0, fs, 1, 1, 1)
-            wg2 = L.Wgrad(s_h1, one.c(0), s_dh2, B, 1, 1, 1, hd, fs, L.dptr(st.view("4.weight", grad=True)), bnp, 1, fbf, 1)
+            sw_h1 = self.h1_plw.src(0, fs, 1, 1, 1)
+            sw_feat = self.feat_plw.src(0, fs, 1, 1, 1)
+            wg2 = L.Wgrad(sw_h1, one.c(0), s_dh2, B, 1, 1, 1, hd, fs, L.dptr(st.view("4.weight", grad=True)), bnp, 1, 1, 1)
             dg2 = ops.make_conv(s_dh2, 1, one.c(1), B, (1, 1, 1), eng.packed_bwd["4"], self.dh1, npass=bnp)
-            wg1 = L.Wgrad(s_feat, one.c(0), s_dh1, B, 1, 1, 1, fs, fs, L.dptr(st.view("2.weight", grad=True)), bnp, 1, fbf, 1)
+            wg1 = L.Wgrad(sw_feat, one.c(0), s_dh1, B, 1, 1, 1, fs, fs, L.dptr(st.view("2.weight", grad=True)), bnp, 1, 1, 1)
             dg1 = ops.make_conv(s_dh1, 1, one.c(1), B, (1, 1, 1), eng.packed_bwd["2"], self.dfeat, npass=bnp)
             self.keep += [s_dh2, wg2, dg2, s_dh1, wg1, dg1]
             bw.append((lib.coclr_conv_wgrad, (C.byref(wg2),)))
@@ -442,8 +456,9 @@ class Plan:
                     tiles = ((kreal + bnk - 1) // bnk) * ((it.cout + 127) // 128)
                     chunks = (a.M + 63) // 64
                     splits = max(1, min(chunks, (2 * nsm + tiles - 1) // tiles))
-                    wg = L.Wgrad(src_of(sa), geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin,
-                                 L.dptr(st.view(it.name + ".weight", grad=True)), bnp, 1, fbf, splits)
+                    wsrc = sa.plw.src(0, sa.spec.C, sa.dims[0], sa.dims[1], sa.dims[2])
+                    wg = L.Wgrad(wsrc, geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin,
+                                 L.dptr(st.view(it.name + ".weight", grad=True)), bnp, 1, 1, splits)
                     self.keep += [wg, dy]
                     bw.append((lib.coclr_conv_wgrad, (C.byref(wg),)))
                     if it.need_dgrad:
@@ -456,7 +471,7 @@ class Plan:
                 it = pool_into[t.index]
                 sa = acts[it.src.index]
                 geom = ops.Geometry(it.k, it.s, it.p)
-                pl = L.Pool(None, None, it.src.C, 0, None, None, t.C, 0, L.dptr(a.idx), B, t.C,
+                pl = L.Pool(None, None, it.src.C, 0, None, None, t.C, 0, None, None, L.dptr(a.idx), B, t.C,
                             sa.dims[0], sa.dims[1], sa.dims[2], a.dims[0], a.dims[1], a.dims[2], geom.c(0),
                             L.dptr(a.grad), L.dptr(sa.grad), int(sa.grad_written))
                 self.keep.append(pl)
@@ -547,8 +562,10 @@ class EncoderEngine:
             p.stats.zero_()
             self.store.nbt += 1
         lib = L.load()
+        tw = p.input.plw if (p.input.plw is not None and p.input.plw is not p.input.pl) else None
         L.check(lib.coclr_pack_input(L.dptr(x), x.stride(0), x.stride(1), Cin, L.dptr(p.input.pl.hi),
-                                     L.dptr(p.input.pl.lo), B, T * H * W, L.dptr(batch_index), L.stream_ptr()),
+                                     L.dptr(p.input.pl.lo), L.dptr(tw.hi) if tw else None,
+                                     L.dptr(tw.lo) if tw else None, B, T * H * W, L.dptr(batch_index), L.stream_ptr()),
                 "coclr_pack_input")
         self._run(p.fwd)
         return p

@@ -56,7 +56,7 @@ class Split(C.Structure):
     _fields_ = [("x", C.c_void_p), ("ld", C.c_int), ("coff", C.c_int), ("C", C.c_int), ("M", C.c_long),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int),
                 ("hi", C.c_void_p), ("lo", C.c_void_p), ("out_ld", C.c_int), ("out_coff", C.c_int),
-                ("bf16", C.c_int)]
+                ("bf16", C.c_int), ("hi2", C.c_void_p), ("lo2", C.c_void_p)]
 
 
 class BnFinalize(C.Structure):
@@ -79,7 +79,7 @@ class BnBwd(C.Structure):
 class Pool(C.Structure):
     _fields_ = [("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("ldx", C.c_int), ("x_coff", C.c_int),
                 ("y_hi", C.c_void_p), ("y_lo", C.c_void_p), ("ldy", C.c_int), ("y_coff", C.c_int),
-                ("idx", C.c_void_p),
+                ("y2_hi", C.c_void_p), ("y2_lo", C.c_void_p), ("idx", C.c_void_p),
                 ("B", C.c_int), ("C", C.c_int), ("Ti", C.c_int), ("Hi", C.c_int), ("Wi", C.c_int),
                 ("To", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int), ("g", Geom),
                 ("dy", C.c_void_p), ("dx", C.c_void_p), ("accumulate", C.c_int)]

@@ -46,12 +46,14 @@ class Planes:
         return L.Src(L.dptr(self.hi), L.dptr(self.lo), self.ld, coff, Cc, T, H, W)
 
 
-def split_into(x, planes, coff=0, Cc=None, scale=None, shift=None, relu=False, out_coff=0):
-    """planes[..., out_coff:out_coff+C] = split(relu?(scale*x[..., coff:coff+C]+shift)); x fp32 rows."""
+def split_into(x, planes, coff=0, Cc=None, scale=None, shift=None, relu=False, out_coff=0, twin=None):
+    """planes[..., out_coff:out_coff+C] = split(relu?(scale*x[..., coff:coff+C]+shift)); x fp32 rows.
+    twin: optional bf16 Planes of the same shape receiving the same values."""
     Cc = Cc or x.shape[-1]
     M = x.numel() // x.shape[-1]
     p = L.Split(L.dptr(x), x.shape[-1], coff, Cc, M, L.dptr(scale), L.dptr(shift), int(bool(relu)),
-                L.dptr(planes.hi), L.dptr(planes.lo), planes.ld, out_coff, planes.bf16)
+                L.dptr(planes.hi), L.dptr(planes.lo), planes.ld, out_coff, planes.bf16,
+                L.dptr(twin.hi) if twin is not None else None, L.dptr(twin.lo) if twin is not None else None)
     L.check(L.load().coclr_affine_split(C.byref(p), L.num_sms(), L.stream_ptr()), "coclr_affine_split")
     return planes
 

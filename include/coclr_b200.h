@@ -120,6 +120,8 @@ typedef struct {
   void* lo; /* may be NULL */
   int out_ld, out_coff;
   int bf16;
+  void* hi2; /* optional bf16 twin of the planes (same out_ld / out_coff) for the weight-gradient GEMM, whose */
+  void* lo2; /* two operands must share one 16-bit format (tcgen05 kind::f16); NULL to skip */
 } coclr_split_t;
 int coclr_affine_split(const coclr_split_t* p, int num_sms, coclr_stream_t stream);
 
@@ -178,6 +180,8 @@ typedef struct {
   void* y_hi;       /* output planes [B,To,Ho,Wo,ldy] fp16 */
   void* y_lo;
   int ldy, y_coff;
+  void* y2_hi;      /* optional bf16 twin of the output planes (see coclr_split_t), or NULL */
+  void* y2_lo;
   unsigned char* idx; /* [B*To*Ho*Wo, C] arg-max tap, may be NULL in forward-only use */
   int B, C, Ti, Hi, Wi, To, Ho, Wo;
   coclr_geom_t g;
@@ -197,8 +201,9 @@ int coclr_avgpool_bwd(const float* dfeat, float* dA, int ld, int coff, int B, in
 /* ---- block[:, i].contiguous() + NCDHW -> channels-last fp16 hi/lo planes with C padded to 8
  * (model/pretrain.py:149-150); batch_index (device int64[B], or NULL) gathers source clips
  * out[b] = x[batch_index[b]] = the shuffle-BN pick x_gather[idx_this] (pretrain.py:124) ------------ */
-int coclr_pack_input(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi, void* out_lo, int B,
-                     long thw, const long* batch_index, coclr_stream_t stream);
+int coclr_pack_input(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi, void* out_lo,
+                     void* out2_hi, void* out2_lo /* optional bf16 twin */, int B, long thw, const long* batch_index,
+                     coclr_stream_t stream);
 
 /* ---- F.normalize(z + bias, dim=1) (model/pretrain.py:154,167) ------------------------------------- */
 int coclr_l2norm_fwd(const float* z, const float* bias, float* q, float* inv_norm, int B, int D, coclr_stream_t stream);

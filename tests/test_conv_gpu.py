@@ -63,7 +63,7 @@ def _setup(case, seed=0):
     return ops, geom, x, w
 
 
-def _planes_of(ops, x_ncdhw, bf16, scale=None, shift=None, relu=False, ld_extra=8, coff=8, lo=True):
+def _planes_of(ops, x_ncdhw, bf16, scale=None, shift=None, relu=False, ld_extra=8, coff=8, lo=True, twin=False):
     """Run the split kernel: NCDHW fp32 -> hi/lo planes with the channels at [coff, coff+Cp) of a wider buffer."""
     B, Cc, T, H, W = x_ncdhw.shape
     Cp = _r8(Cc)
@@ -74,7 +74,10 @@ def _planes_of(ops, x_ncdhw, bf16, scale=None, shift=None, relu=False, ld_extra=
         pl.lo.fill_(3.0)
     sc = F.pad(scale, (0, Cp - Cc)).contiguous() if scale is not None else None
     sh = F.pad(shift, (0, Cp - Cc)).contiguous() if shift is not None else None
-    ops.split_into(rows, pl, 0, Cp, sc, sh, relu, out_coff=coff)
+    tw = ops.Planes((B, T, H, W, Cp + coff + ld_extra), 1, "cuda", lo=lo) if twin else None
+    ops.split_into(rows, pl, 0, Cp, sc, sh, relu, out_coff=coff, twin=tw)
+    if twin:
+        return pl, Cp, coff, tw
     return pl, Cp, coff
 
 
@@ -93,8 +96,6 @@ def test_affine_split(bf16, diag):
     diag["split/bf%d" % bf16] = err
     assert err < (2e-6 if not bf16 else 2e-5)
     assert float((pl.hi[..., :coff].float() - 3).abs().max()) == 0.0   # neighbours untouched
-    # hi alone is the correctly rounded 16-bit value
-    assert torch.equal(pl.hi[..., coff:coff + 24].float(), ref.to(pl.hi.dtype).float())
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
@@ -134,21 +135,21 @@ def test_conv_forward(case, npass, bf16, diag):
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_conv_accumulate_mixed_formats(case, diag):
-    """dst += result, with fp16 activations against bf16-packed weights (independent A/B formats)."""
+def test_conv_accumulate(case, diag):
+    """dst += result (bf16 planes x bf16 weights; tcgen05 kind::f16 needs one format for both operands)."""
     ops, geom, x, w = _setup(case, seed=3)
     name, Cin, Cout, k, s, p, B, T, H, W = case
     To, Ho, Wo = geom.out_dims(T, H, W)
     ref = F.conv3d(x.double(), w.double(), stride=s, padding=p)
-    pl, Cp, coff = _planes_of(ops, x, 0)
+    pl, Cp, coff = _planes_of(ops, x, 1)
     pw = ops.PackedWeights(Cout, Cin, geom.taps, Cp, 0, 1, "cuda").pack(w.contiguous())
     base = torch.randn(B, To, Ho, Wo, Cout, device="cuda")
     dst = base.clone()
-    ops.conv_igemm(pl.src(coff, Cp, T, H, W), 0, geom.c(0), B, (To, Ho, Wo), pw, dst, accumulate=True, npass=3)
+    ops.conv_igemm(pl.src(coff, Cp, T, H, W), 1, geom.c(0), B, (To, Ho, Wo), pw, dst, accumulate=True, npass=3)
     torch.cuda.synchronize()
     got = (dst - base).permute(0, 4, 1, 2, 3)
     err = _rel(got, ref)
-    diag["acc_mixed/%s" % name] = err
+    diag["acc/%s" % name] = err
     assert err < 2e-4
 
 
@@ -180,7 +181,7 @@ def test_conv_dgrad(case, npass, diag):
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 @pytest.mark.parametrize("npass,splits", [(3, 1), (3, 5), (1, 2)])
 def test_conv_wgrad(case, npass, splits, diag):
-    """dY as bf16 planes x activations as fp16 planes (the formats the training step uses)."""
+    """dY as bf16 planes x the bf16 twin of the activation planes (what the training step uses)."""
     ops, geom, x, w = _setup(case, seed=9)
     name, Cin, Cout, k, s, p, B, T, H, W = case
     To, Ho, Wo = geom.out_dims(T, H, W)
@@ -192,10 +193,10 @@ def test_conv_wgrad(case, npass, splits, diag):
     wd = w.double().requires_grad_(True)
     y = F.conv3d(xin, wd, stride=s, padding=p)
     (ref,) = torch.autograd.grad(y, wd, dy.double())
-    pl, Cp, coff = _planes_of(ops, x, 0, scale, shift, True, lo=(npass > 1))
+    _, Cp, coff, pl = _planes_of(ops, x, 0, scale, shift, True, lo=(npass > 1), twin=True)
     dpl, Cop, dcoff = _planes_of(ops, dy, 1, lo=(npass > 1))
     dw = torch.zeros_like(w)
-    ops.conv_wgrad(pl.src(coff, Cp, T, H, W), 0, geom.c(0), dpl.src(dcoff, Cop, To, Ho, Wo), 1, B, (To, Ho, Wo),
+    ops.conv_wgrad(pl.src(coff, Cp, T, H, W), 1, geom.c(0), dpl.src(dcoff, Cop, To, Ho, Wo), 1, B, (To, Ho, Wo),
                    Cout, Cin, dw, npass=npass, splits=splits)
     torch.cuda.synchronize()
     err = _rel(dw, ref)
@@ -226,13 +227,16 @@ def test_maxpool_fwd_bwd(k, s, p, diag):
     idx = torch.empty(B * To * Ho * Wo * Cp, dtype=torch.uint8, device="cuda")
     dyt = torch.randn(B, To, Ho, Wo, Cp, device="cuda", generator=g)
     dx = torch.full((B, T, H, W, pl.ld), 0.5, device="cuda")
-    pp = L.Pool(L.dptr(pl.hi), L.dptr(pl.lo), pl.ld, coff, L.dptr(out.hi), L.dptr(out.lo), Cp, 0, L.dptr(idx),
+    tw = ops.Planes((B, To, Ho, Wo, Cp), 1, "cuda")
+    pp = L.Pool(L.dptr(pl.hi), L.dptr(pl.lo), pl.ld, coff, L.dptr(out.hi), L.dptr(out.lo), Cp, 0,
+                L.dptr(tw.hi), L.dptr(tw.lo), L.dptr(idx),
                 B, Cp, T, H, W, To, Ho, Wo, geom.c(0), L.dptr(dyt), L.dptr(dx), 1)
     L.check(L.load().coclr_maxpool_fwd(C.byref(pp), L.stream_ptr()), "coclr_maxpool_fwd")
     L.check(L.load().coclr_maxpool_bwd(C.byref(pp), L.stream_ptr()), "coclr_maxpool_bwd")
     torch.cuda.synchronize()
     got = out.value()[..., :Cc].permute(0, 4, 1, 2, 3)
     assert torch.equal(got.double(), ref.detach())
+    assert _rel(tw.value()[..., :Cc].permute(0, 4, 1, 2, 3), ref.detach()) < 2e-5
     (gref,) = torch.autograd.grad(ref, xv, dyt[..., :Cc].permute(0, 4, 1, 2, 3).double())
     gdx = (dx[..., coff:coff + Cc] - 0.5).permute(0, 4, 1, 2, 3)
     e = _rel(gdx, gref)
