@@ -308,8 +308,15 @@ def main():
                     desc = "M=%d Cout=%d K=%d splits=%d" % (o.B * o.Td * o.Hd * o.Wd, o.Cout,
                                                            o.g.kt * o.g.kh * o.g.kw * o.src.C, o.splits)
                 rows.append((msl, name, desc, fl / (msl * 1e-3) / 1e12))
+            elif name in ("coclr_maxpool_fwd", "coclr_maxpool_bwd"):
+                o = a[0]._obj
+                rows.append((s0.elapsed_time(s1), name, "C=%d in=%dx%dx%d k=%d%d%d s=%d%d%d" % (
+                    o.C, o.Ti, o.Hi, o.Wi, o.g.kt, o.g.kh, o.g.kw, o.g.st, o.g.sh, o.g.sw), 0.0))
+            elif name in ("coclr_bn_bwd", "coclr_affine_split"):
+                o = a[0]._obj
+                rows.append((s0.elapsed_time(s1), name, "M=%d C=%d" % (o.M, o.C), 0.0))
         rows.sort(reverse=True)
-        for msl, name, desc, tf in rows[:40]:
+        for msl, name, desc, tf in rows[:60]:
             print("%8.3f ms %-18s %-40s %7.1f TF/s" % (msl, name[6:], desc, tf), file=sys.stderr)
 
     if rank == 0:

@@ -302,9 +302,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
         if (col_ok && rows_here > 0) {
           float* d = P.dst + (size_t)row_base * P.dst_ld + P.dst_coff + col;
           if (P.accumulate) {
-            for (int r = 0; r < rows_here; ++r, d += P.dst_ld) {
-              const float val = my_stage[r * kStagePitch + lane] * us + *d;
-              *d = val;
+            // read-modify-write: batch the loads (8 in flight per lane) instead of one dependent load per row
+            for (int r0 = 0; r0 < rows_here; r0 += 8) {
+              float old[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) old[j] = (r0 + j < rows_here) ? d[(size_t)(r0 + j) * P.dst_ld] : 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (r0 + j < rows_here)
+                  d[(size_t)(r0 + j) * P.dst_ld] = fmaf(my_stage[(r0 + j) * kStagePitch + lane], us, old[j]);
             }
           } else {
 #pragma unroll 8
