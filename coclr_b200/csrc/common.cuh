@@ -83,6 +83,11 @@ COCLR_DEVINL void cp_async16(uint32_t smem_dst, const void* gmem_src, uint32_t s
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes)
                : "memory");
 }
+// The mbarrier receives one arrival from this thread once all cp.async it has issued so far have landed
+// (.noinc: the arrival is part of the barrier's expected count) -- no waiting in the producer thread.
+COCLR_DEVINL void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 COCLR_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending>
 COCLR_DEVINL void cp_async_wait() {

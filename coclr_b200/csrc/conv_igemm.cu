@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
-      mbar_init(&full_bar[s], kProducerWarps + 1);
+      mbar_init(&full_bar[s], kProducerWarps * 32 + 1);  // every producer thread (async, via cp.async) + the weight loader
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -188,7 +188,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
     const int r0 = pt >> 3;  // 0..31; rows r0 + 32*i
     const uint32_t smem_base = smem_u32(smem);
     uint32_t stage = 0, phase = 0;
-    int prev_stage = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / P.n_tiles;
       int rb[4], rt[4], ry[4], rx[4];
@@ -199,23 +198,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         const uint32_t sa = smem_base + stage * L.stage_bytes;
         gather_block_async<kLo, 4>(P.src, P.g, P.Kreal, kc * kChunkK, ck, r0, rb, rt, ry, rx, sa, sa + L.a_bytes);
-        cp_async_commit();
-        if (prev_stage >= 0) {
-          // the previous chunk has landed once at most one group (this one) is still in flight
-          cp_async_wait<1>();
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full_bar[prev_stage]);
-        }
-        prev_stage = (int)stage;
+        // asynchronous arrival when this thread's copies have landed: the producer never waits for data
+        cp_async_mbar_arrive_noinc(&full_bar[stage]);
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
-    }
-    if (prev_stage >= 0) {
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[prev_stage]);
     }
   } else if (warp == 13) {
     // ===================== weight loader (bulk copies) =====================
@@ -420,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
-      mbar_init(&full_bar[s], kProducerWarps);
+      mbar_init(&full_bar[s], kProducerWarps * 32);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&tfull_bar[0], 1);
@@ -438,7 +424,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
     const int r0 = pt >> 3;  // rows r0 + 32*i, i < 2
     const uint32_t smem_base = smem_u32(smem);
     uint32_t stage = 0, phase = 0;
-    int prev_stage = -1;
     coclr_geom_t ident;
     ident.kt = ident.kh = ident.kw = 1;
     ident.st = ident.sh = ident.sw = 1;
@@ -466,21 +451,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
         gather_block_async<kLo, 2>(P.src, P.g, Kreal, k_tile * BNk + blk * 64, ck, r0, rb, rt, ry, rx,
                                    s_a + blk * (kWgPx * 128), s_a + L.a_bytes + blk * (kWgPx * 128));
       }
-      cp_async_commit();
-      if (prev_stage >= 0) {
-        cp_async_wait<1>();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[prev_stage]);
-      }
-      prev_stage = (int)stage;
+      cp_async_mbar_arrive_noinc(&full_bar[stage]);
       if (++stage == nstages) { stage = 0; phase ^= 1u; }
-    }
-    if (prev_stage >= 0) {
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[prev_stage]);
     }
   } else if (warp == 12) {
     const uint32_t idesc = make_idesc(P.dy_bf16 ? 1u : 0u, P.src_bf16 ? 1u : 0u, 1u, 1u, 128u, (uint32_t)BNk);

@@ -1,0 +1,50 @@
+"""Profiling helper (test infrastructure): runs one implicit-GEMM conv launch shape repeatedly so that ncu can
+capture it.  python tests/tools/run_one_conv.py fwd|dgrad|wgrad Cin Cout kt kh kw B T H W [npass] [iters]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from coclr_b200 import ops  # noqa: E402
+
+mode = sys.argv[1]
+Cin, Cout, kt, kh, kw, B, T, H, W = [int(v) for v in sys.argv[2:11]]
+npass = int(sys.argv[11]) if len(sys.argv) > 11 else 3
+iters = int(sys.argv[12]) if len(sys.argv) > 12 else 5
+geom = ops.Geometry((kt, kh, kw), (1, 1, 1), (kt // 2, kh // 2, kw // 2))
+dev = "cuda"
+r8 = lambda c: (c + 7) // 8 * 8
+w = torch.randn(Cout, Cin, kt, kh, kw, device=dev) * 0.05
+if mode == "fwd":
+    x = ops.Planes((B, T, H, W, r8(Cin)), 0, dev)
+    x.hi.normal_(); x.lo.normal_(0, 1e-3)
+    pw = ops.PackedWeights(Cout, Cin, geom.taps, r8(Cin), 0, 0, dev).pack(w)
+    dst = torch.empty(B, T, H, W, Cout, device=dev)
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
+    run = lambda: ops.conv_igemm(x.src(0, r8(Cin), T, H, W), 0, geom.c(0), B, (T, H, W), pw, dst, stats=stats, npass=npass)
+elif mode == "dgrad":
+    dy = ops.Planes((B, T, H, W, r8(Cout)), 1, dev)
+    dy.hi.normal_(); dy.lo.normal_(0, 1e-3)
+    pw = ops.PackedWeights(Cout, Cin, geom.taps, r8(Cout), 1, 1, dev).pack(w)
+    dst = torch.zeros(B, T, H, W, Cin, device=dev)
+    run = lambda: ops.conv_igemm(dy.src(0, r8(Cout), T, H, W), 1, geom.c(1), B, (T, H, W), pw, dst, accumulate=False, npass=npass)
+else:
+    x = ops.Planes((B, T, H, W, r8(Cin)), 1, dev)
+    x.hi.normal_(); x.lo.normal_(0, 1e-3)
+    dy = ops.Planes((B, T, H, W, r8(Cout)), 1, dev)
+    dy.hi.normal_(); dy.lo.normal_(0, 1e-3)
+    dw = torch.zeros_like(w)
+    splits = int(os.environ.get("SPLITS", "50"))
+    run = lambda: ops.conv_wgrad(x.src(0, r8(Cin), T, H, W), 1, geom.c(0), dy.src(0, r8(Cout), T, H, W), 1, B, (T, H, W),
+                                 Cout, Cin, dw, npass=npass, splits=splits)
+for _ in range(2):
+    run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(iters):
+    run()
+e1.record()
+torch.cuda.synchronize()
+print("%s %s: %.3f ms/launch" % (mode, sys.argv[2:11], e0.elapsed_time(e1) / iters))
