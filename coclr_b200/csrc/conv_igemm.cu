@@ -39,12 +39,23 @@ COCLR_DEVINL void row_coords(const coclr_geom_t& G, int Td, int Hd, int Wd, int 
     t = y = x = 0;
     return;
   }
-  int xx = m % Wd;
-  int r = m / Wd;
-  int yy = r % Hd;
-  r /= Hd;
-  int tt = r % Td;
-  b = r / Td;
+  int xx, yy, tt;
+  if (((Wd & (Wd - 1)) | (Hd & (Hd - 1)) | (Td & (Td - 1))) == 0) {  // power-of-two grid: shifts, no division
+    const int sw = __ffs(Wd) - 1, sh = __ffs(Hd) - 1, st = __ffs(Td) - 1;
+    xx = m & (Wd - 1);
+    int r = m >> sw;
+    yy = r & (Hd - 1);
+    r >>= sh;
+    tt = r & (Td - 1);
+    b = r >> st;
+  } else {
+    xx = m % Wd;
+    int r = m / Wd;
+    yy = r % Hd;
+    r /= Hd;
+    tt = r % Td;
+    b = r / Td;
+  }
   if (!G.transposed) {
     t = tt * G.st - G.pt;
     y = yy * G.sh - G.ph;
@@ -59,22 +70,44 @@ COCLR_DEVINL void row_coords(const coclr_geom_t& G, int Td, int Hd, int Wd, int 
 // Issue the cp.async copies of NI*32 rows x 64 K-columns [kbase, kbase+64) of the implicit operand into one
 // swizzled [rows][128 B] block (hi plane) and its lo twin.  Thread (ck, r0) owns the 16-byte chunk ck
 // (8 consecutive K elements) of rows r0 + 32*i.  K index k = tap*C + channel, C % 8 == 0.
-template <bool kLo, int NI>
-COCLR_DEVINL void gather_block_async(const coclr_src_t& S, const coclr_geom_t& G, int Kreal, int kbase, int ck, int r0,
-                                     const int* rb, const int* rt, const int* ry, const int* rx, uint32_t blk_hi,
-                                     uint32_t blk_lo) {
-  const int k0 = kbase + ck * 8;
-  const bool kvalid = k0 < Kreal;
-  int ta = 0, ya = 0, xa = 0, ci = 0;
-  if (kvalid) {
-    int tap = k0 / S.C;
-    ci = k0 - tap * S.C;
-    int khw = G.kh * G.kw;
-    ta = tap / khw;
-    int rem = tap - ta * khw;
-    ya = rem / G.kw;
-    xa = rem - ya * G.kw;
+// Position of one 16-byte K granule in (tap, channel) space; kept per thread and advanced incrementally so the
+// pipelined loops never divide.
+struct TapPos {
+  int k0, ta, ya, xa, ci;
+};
+COCLR_DEVINL TapPos tap_of(const coclr_src_t& S, const coclr_geom_t& G, int k0) {
+  TapPos p;
+  p.k0 = k0;
+  const int tap = k0 / S.C;
+  p.ci = k0 - tap * S.C;
+  const int khw = G.kh * G.kw;
+  p.ta = tap / khw;
+  const int rem = tap - p.ta * khw;
+  p.ya = rem / G.kw;
+  p.xa = rem - p.ya * G.kw;
+  return p;
+}
+COCLR_DEVINL void tap_advance(TapPos& p, const coclr_src_t& S, const coclr_geom_t& G, int step) {
+  p.k0 += step;
+  p.ci += step;
+  while (p.ci >= S.C) {
+    p.ci -= S.C;
+    if (++p.xa == G.kw) {
+      p.xa = 0;
+      if (++p.ya == G.kh) {
+        p.ya = 0;
+        ++p.ta;
+      }
+    }
   }
+}
+
+template <bool kLo, int NI>
+COCLR_DEVINL void gather_block_async(const coclr_src_t& S, const coclr_geom_t& G, int Kreal, const TapPos& tp, int ck,
+                                     int r0, const int* rb, const int* rt, const int* ry, const int* rx,
+                                     uint32_t blk_hi, uint32_t blk_lo) {
+  const bool kvalid = tp.k0 < Kreal;
+  const int ta = tp.ta, ya = tp.ya, xa = tp.xa, ci = tp.ci;
   const uint16_t* hi = reinterpret_cast<const uint16_t*>(S.hi);
   const uint16_t* lo = reinterpret_cast<const uint16_t*>(S.lo);
 #pragma unroll
@@ -188,16 +221,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
     const int r0 = pt >> 3;  // 0..31; rows r0 + 32*i
     const uint32_t smem_base = smem_u32(smem);
     uint32_t stage = 0, phase = 0;
+    const TapPos tap0 = tap_of(P.src, P.g, ck * 8);  // this thread's K granule in chunk 0 (the only division)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / P.n_tiles;
       int rb[4], rt[4], ry[4], rx[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         row_coords(P.g, P.Td, P.Hd, P.Wd, M, m_tile * kTileM + r0 + 32 * i, rb[i], rt[i], ry[i], rx[i]);
+      TapPos tp = tap0;
       for (int kc = 0; kc < nkc; ++kc) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         const uint32_t sa = smem_base + stage * L.stage_bytes;
-        gather_block_async<kLo, 4>(P.src, P.g, P.Kreal, kc * kChunkK, ck, r0, rb, rt, ry, rx, sa, sa + L.a_bytes);
+        gather_block_async<kLo, 4>(P.src, P.g, P.Kreal, tp, ck, r0, rb, rt, ry, rx, sa, sa + L.a_bytes);
+        tap_advance(tp, P.src, P.g, kChunkK);
         // asynchronous arrival when this thread's copies have landed: the producer never waits for data
         cp_async_mbar_arrive_noinc(&full_bar[stage]);
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
@@ -429,14 +465,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
     ident.st = ident.sh = ident.sw = 1;
     ident.pt = ident.ph = ident.pw = 0;
     ident.transposed = 0;
+    // the K granules this thread copies are the same for every pixel chunk: decompose them once
+    TapPos tp_dy[2], tp_a[4];
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) tp_dy[blk] = tap_of(P.dy, ident, c_tile * 128 + blk * 64 + ck * 8);
+#pragma unroll
+    for (int blk = 0; blk < 4; ++blk) tp_a[blk] = tap_of(P.src, P.g, k_tile * BNk + blk * 64 + ck * 8);
     for (int ch = ch_begin; ch < ch_begin + nch; ++ch) {
       int rb[2], rt[2], ry[2], rx[2];    // source-space bases for the activation gather
       int qb[2], qt[2], qy[2], qx[2];    // plain destination coordinates for dY
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int m = ch * kWgPx + r0 + 32 * i;
-        row_coords(P.g, P.Td, P.Hd, P.Wd, M, m, rb[i], rt[i], ry[i], rx[i]);
         row_coords(ident, P.Td, P.Hd, P.Wd, M, m, qb[i], qt[i], qy[i], qx[i]);
+        rb[i] = qb[i];
+        rt[i] = qt[i] * P.g.st - P.g.pt;
+        ry[i] = qy[i] * P.g.sh - P.g.ph;
+        rx[i] = qx[i] * P.g.sw - P.g.pw;
       }
       mbar_wait(&empty_bar[stage], phase ^ 1u);
       const uint32_t s_dy = smem_base + stage * L.stage_bytes;
@@ -444,12 +489,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
       // dY: 2 blocks of 64 output channels
 #pragma unroll
       for (int blk = 0; blk < 2; ++blk) {
-        gather_block_async<kLo, 2>(P.dy, ident, P.dy.C, c_tile * 128 + blk * 64, ck, r0, qb, qt, qy, qx,
+        gather_block_async<kLo, 2>(P.dy, ident, P.dy.C, tp_dy[blk], ck, r0, qb, qt, qy, qx,
                                    s_dy + blk * (kWgPx * 128), s_dy + L.dy_bytes + blk * (kWgPx * 128));
       }
-      for (int blk = 0; blk < BNk / 64; ++blk) {
-        gather_block_async<kLo, 2>(P.src, P.g, Kreal, k_tile * BNk + blk * 64, ck, r0, rb, rt, ry, rx,
-                                   s_a + blk * (kWgPx * 128), s_a + L.a_bytes + blk * (kWgPx * 128));
+#pragma unroll
+      for (int blk = 0; blk < 4; ++blk) {
+        if (blk < BNk / 64)
+          gather_block_async<kLo, 2>(P.src, P.g, Kreal, tp_a[blk], ck, r0, rb, rt, ry, rx,
+                                     s_a + blk * (kWgPx * 128), s_a + L.a_bytes + blk * (kWgPx * 128));
       }
       cp_async_mbar_arrive_noinc(&full_bar[stage]);
       if (++stage == nstages) { stage = 0; phase ^= 1u; }
