@@ -31,9 +31,9 @@ def concat_all_gather(tensor):
     world, _ = _world()
     if world == 1:
         return tensor
-    out = torch.empty((world,) + tuple(tensor.shape), dtype=tensor.dtype, device=tensor.device)
+    out = torch.empty((world * tensor.shape[0],) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
     dist.all_gather_into_tensor(out, tensor.contiguous())
-    return out.view((-1,) + tuple(tensor.shape[1:]))
+    return out
 
 
 class _EncodeFn(torch.autograd.Function):
