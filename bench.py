@@ -81,7 +81,9 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 def cpu_oracle_clips_per_s(batch, seq_len, img, K, steps, warmup):
     from oracle import coclr_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    nthreads = int(os.environ.get("COCLR_CPU_THREADS", "0"))
+    if nthreads > 0:
+        torch.set_num_threads(nthreads)
     torch.manual_seed(0)
     sd = O.synth_state(O.infonce_shapes(128, K), seed=0)
     for k in O.param_keys(sd, "encoder_q."):
@@ -103,25 +105,28 @@ def cpu_oracle_clips_per_s(batch, seq_len, img, K, steps, warmup):
             times.append(dt)
     times.sort()
     med = times[len(times) // 2]
-    return 2.0 * batch / med, med
+    # clips are counted in units of the benchmark's 32-frame clip: a pair of `seq_len`-frame clips is
+    # 2 * seq_len / 32 of them (conv work is linear in the number of frames)
+    return 2.0 * batch * (seq_len / float(CFG["seq_len"])) / med, med
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 2
+    batch, sample_T = 1, 8
     steps = max(1, min(args.steps, 3))
-    val, med = cpu_oracle_clips_per_s(batch, args.seq_len, CFG["img"], CFG["K"], steps, 1)
+    val, med = cpu_oracle_clips_per_s(batch, sample_T, CFG["img"], CFG["K"], steps, 1)
     line = {"impl": "reference", "metric": "clips/sec S3D InfoNCE (32x128^2, K=2048)", "value": val, "unit": "clips/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": med * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "InfoNCE S3D K=2048 seq_len=%d 128^2 full train step (fwd+bwd+Adam)" % args.seq_len,
-                       "batch_per_step": batch},
+            "config": {"workload": "InfoNCE S3D moco-k=2048 128^2 full train step (fwd+bwd+Adam), bounded sample: "
+                                   "%d clip pair(s) of %d frames per step, scaled to 32-frame clips" % (batch, sample_T),
+                       "batch_per_step": batch, "sample_seq_len": sample_T},
             "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "oracle port of the reference (torch CPU fp32), %d timed steps of batch %d "
-                                       "clip pairs after 1 warm-up; reference is pure Python and cannot travel"
-                                       % (steps, batch)},
+                             "sample": "oracle port of the reference (torch CPU fp32), %d timed steps of %d pair(s) of "
+                                       "%d-frame 128^2 clips after 1 warm-up, counted as %d/32 clips each; the reference "
+                                       "is pure Python and cannot travel to the GPU box" % (steps, batch, sample_T, sample_T)},
             "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -135,7 +140,7 @@ def conv_flops(cv):
         pix = cv.B * cv.src.T * cv.src.H * cv.src.W
         return 2.0 * pix * cv.N * cv.g.kt * cv.g.kh * cv.g.kw * cv.src.C
     pix = cv.B * cv.Td * cv.Hd * cv.Wd
-    cin = 3 if cv.src.C == 4 else cv.src.C   # RGB stem is stored with a zero 4th channel
+    cin = 3 if cv.src.C == 8 else cv.src.C   # the RGB stem input is stored with 5 zero channels (C padded to 8)
     return 2.0 * pix * cv.N * cv.g.kt * cv.g.kh * cv.g.kw * cin
 
 
@@ -227,7 +232,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t)
-    final_loss = float(loss_keep[0])
+    final_loss = float(loss_keep[0].detach())
     value = 2.0 * B * world / (ms * 1e-3)
 
     # ---- end to end: pinned host inputs, H2D inside the timed region (prefetched), loss read back every step ----
@@ -323,9 +328,10 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             try:
-                v, med = cpu_oracle_clips_per_s(2, T, HW, K, 2, 1)
+                v, med = cpu_oracle_clips_per_s(1, 8, HW, K, 2, 1)
                 cpu = {"value": v, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
-                       "sample": "oracle port (torch CPU fp32) full train step, batch 2 clip pairs, 2 timed steps after 1 warm-up"}
+                       "sample": "oracle port (torch CPU fp32) full train step on 1 pair of 8-frame 128^2 clips "
+                                 "(= 0.5 clip of 32 frames), 2 timed steps after 1 warm-up, %.1f s/step" % med}
             except Exception as ex:  # pragma: no cover
                 cpu = {"value": None, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
                        "sample": "failed: %r" % (ex,)}
