@@ -79,11 +79,23 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm restated in oracle/ (the Python reference itself cannot travel to the GPU box)
 # ------------------------------------------------------------------------------------------------
+def usable_cores():
+    """Host threads this process may really use: the cgroup CPU quota when there is one (oversubscribing it makes
+    the CPU arm several times slower), else the affinity mask."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(round(int(quota) / int(period)))))
+    except Exception:
+        pass
+    env = int(os.environ.get("COCLR_CPU_THREADS", "0"))
+    return env if env > 0 else n
+
+
 def cpu_oracle_clips_per_s(batch, seq_len, img, K, steps, warmup):
     from oracle import coclr_oracle as O
-    nthreads = int(os.environ.get("COCLR_CPU_THREADS", "0"))
-    if nthreads > 0:
-        torch.set_num_threads(nthreads)
+    torch.set_num_threads(usable_cores())
     torch.manual_seed(0)
     sd = O.synth_state(O.infonce_shapes(128, K), seed=0)
     for k in O.param_keys(sd, "encoder_q."):
