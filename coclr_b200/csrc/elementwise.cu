@@ -113,6 +113,73 @@ __global__ void __launch_bounds__(256) affine_split_kernel(const coclr_split_t P
 // ------------------------------------------------------------------------------------------------
 static constexpr int kColThreads = 256;
 
+// BatchNorm finalize fused with apply + ReLU + split: every thread derives (scale, shift) of its own 4 channels
+// from the statistics; block 0 also publishes them (backward needs scale/shift/mean/rstd) and updates the running
+// statistics.  Same column mapping as the BN backward kernels.
+template <bool kBf16>
+__global__ void __launch_bounds__(kColThreads) bn_apply_split_kernel(const coclr_split_t P) {
+  const int C4 = P.C >> 2;
+  const int A = (kColThreads / C4) * C4;
+  const int R = A / C4;
+  const int t = threadIdx.x;
+  if (t >= A) return;
+  const int cg = t % C4, rs = t / C4;
+  const int c = cg * 4;
+  const coclr_bn_finalize_t& F = P.bn;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float mean, var;
+    if (F.training) {
+      const double n = (double)F.count;
+      const double m = F.sum[c + j] / n;
+      double v = F.sumsq[c + j] / n - m * m;
+      if (v < 0.0) v = 0.0;
+      mean = (float)m;
+      var = (float)v;
+      if (blockIdx.x == 0 && rs == 0) {
+        const float unbiased = (float)(F.count > 1 ? v * n / (n - 1.0) : v);
+        F.running_mean[c + j] = (1.f - F.momentum) * F.running_mean[c + j] + F.momentum * mean;
+        F.running_var[c + j] = (1.f - F.momentum) * F.running_var[c + j] + F.momentum * unbiased;
+      }
+    } else {
+      mean = F.running_mean[c + j];
+      var = F.running_var[c + j];
+    }
+    const float rstd = 1.f / sqrtf(var + F.eps);
+    sc[j] = F.gamma[c + j] * rstd;
+    sh[j] = F.beta[c + j] - mean * sc[j];
+    if (blockIdx.x == 0 && rs == 0) {
+      F.scale[c + j] = sc[j];
+      F.shift[c + j] = sh[j];
+      if (F.save_mean) F.save_mean[c + j] = mean;
+      if (F.save_rstd) F.save_rstd[c + j] = rstd;
+    }
+  }
+  uint16_t* hi = reinterpret_cast<uint16_t*>(P.hi);
+  uint16_t* lo = reinterpret_cast<uint16_t*>(P.lo);
+  const long rows_per = ((long)P.M + gridDim.x - 1) / gridDim.x;
+  const long r_begin = (long)blockIdx.x * rows_per;
+  const long r_end = min((long)P.M, r_begin + rows_per);
+  for (long r = r_begin + rs; r < r_end; r += R) {
+    float4 v = ld4(P.x + r * P.ld + P.coff + c);
+    v.x = fmaf(v.x, sc[0], sh[0]);
+    v.y = fmaf(v.y, sc[1], sh[1]);
+    v.z = fmaf(v.z, sc[2], sh[2]);
+    v.w = fmaf(v.w, sc[3], sh[3]);
+    if (P.relu) {
+      v.x = fmaxf(v.x, 0.f);
+      v.y = fmaxf(v.y, 0.f);
+      v.z = fmaxf(v.z, 0.f);
+      v.w = fmaxf(v.w, 0.f);
+    }
+    const size_t o = (size_t)(r * P.out_ld + P.out_coff + c);
+    st_pair4<kBf16>(hi, lo, o, v);
+    if (P.hi2 != nullptr)
+      st_pair4<true>(reinterpret_cast<uint16_t*>(P.hi2), reinterpret_cast<uint16_t*>(P.lo2), o, v);
+  }
+}
+
 // BN backward, phase 1: s1[c] = sum dz, s2[c] = sum dz * xhat, dz = dA * [scale*y+shift > 0]
 __global__ void __launch_bounds__(kColThreads) bn_bwd_reduce_kernel(const coclr_bn_bwd_t P) {
   const int C4 = P.C >> 2;
@@ -523,6 +590,20 @@ extern "C" int coclr_affine_split(const coclr_split_t* p, int num_sms, coclr_str
   if (!p || !p->x || !p->hi || p->C % 4 || p->ld % 4 || p->coff % 4 || p->out_ld % 4 || p->out_coff % 4)
     return COCLR_E_ARG;
   const long total = p->M * (p->C / 4);
+  if (p->bn.scale != nullptr) {  // fused BatchNorm finalize
+    const coclr_bn_finalize_t& f = p->bn;
+    if (!f.shift || !f.gamma || !f.beta || !f.running_mean || !f.running_var || p->C > 1024) return COCLR_E_ARG;
+    if (f.training && (!f.sum || !f.sumsq || f.count <= 0)) return COCLR_E_ARG;
+    const int R = kColThreads / (p->C / 4);
+    long slabs = (p->M + (long)R * 16 - 1) / ((long)R * 16);
+    int grid = (int)(slabs < (long)num_sms * 8 ? slabs : (long)num_sms * 8);
+    if (grid < 1) grid = 1;
+    if (p->bf16)
+      bn_apply_split_kernel<true><<<grid, kColThreads, 0, (cudaStream_t)stream>>>(*p);
+    else
+      bn_apply_split_kernel<false><<<grid, kColThreads, 0, (cudaStream_t)stream>>>(*p);
+    return LAUNCH_OK();
+  }
   const int grid = grid_for(total, 256, num_sms * 16);
   if (p->bf16)
     affine_split_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);

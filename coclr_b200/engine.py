@@ -314,10 +314,11 @@ class Plan:
                 return None, None
             return L.dptr(plw.hi), L.dptr(plw.lo)
 
-        def split_op(x, planes, M, Cc, scale, shift, relu, twin=None):
+        def split_op(x, planes, M, Cc, scale, shift, relu, twin=None, bn=None):
             t_hi, t_lo = twin_ptrs(planes, twin)
             sp = L.Split(L.dptr(x), x.shape[-1], 0, Cc, M, L.dptr(scale), L.dptr(shift), int(bool(relu)),
-                         L.dptr(planes.hi), L.dptr(planes.lo), planes.ld, 0, planes.bf16, t_hi, t_lo)
+                         L.dptr(planes.hi), L.dptr(planes.lo), planes.ld, 0, planes.bf16, t_hi, t_lo,
+                         bn if bn is not None else L.BnFinalize())
             self.keep.append(sp)
             return (lib.coclr_affine_split, (C.byref(sp), nsm))
 
@@ -355,9 +356,8 @@ class Plan:
                                   L.dptr(st.running_mean[rboff:]), L.dptr(st.running_var[rboff:]),
                                   BN_MOMENTUM, BN_EPS, int(training), L.dptr(a.scale), L.dptr(a.shift),
                                   L.dptr(a.mean), L.dptr(a.rstd), it.C)
-                self.keep.append(bf)
-                self.fwd.append((lib.coclr_bn_finalize, (C.byref(bf),)))
-                self.fwd.append(split_op(a.data, a.pl, a.M, it.C, a.scale, a.shift, it.relu, a.plw))
+                # BatchNorm finalize is fused into the apply+split launch
+                self.fwd.append(split_op(a.data, a.pl, a.M, it.C, None, None, it.relu, a.plw, bn=bf))
         # ---- head ----
         out = acts[g.backbone_out.index]
         self.backbone_out = out

@@ -52,13 +52,6 @@ class Pack(C.Structure):
                 ("wpk", C.c_void_p), ("unscale", C.c_void_p)]
 
 
-class Split(C.Structure):
-    _fields_ = [("x", C.c_void_p), ("ld", C.c_int), ("coff", C.c_int), ("C", C.c_int), ("M", C.c_long),
-                ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int),
-                ("hi", C.c_void_p), ("lo", C.c_void_p), ("out_ld", C.c_int), ("out_coff", C.c_int),
-                ("bf16", C.c_int), ("hi2", C.c_void_p), ("lo2", C.c_void_p)]
-
-
 class BnFinalize(C.Structure):
     _fields_ = [("sum", C.c_void_p), ("sumsq", C.c_void_p), ("count", C.c_long),
                 ("gamma", C.c_void_p), ("beta", C.c_void_p),
@@ -66,6 +59,13 @@ class BnFinalize(C.Structure):
                 ("momentum", C.c_float), ("eps", C.c_float), ("training", C.c_int),
                 ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("save_mean", C.c_void_p), ("save_rstd", C.c_void_p), ("C", C.c_int)]
+
+
+class Split(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("ld", C.c_int), ("coff", C.c_int), ("C", C.c_int), ("M", C.c_long),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int),
+                ("hi", C.c_void_p), ("lo", C.c_void_p), ("out_ld", C.c_int), ("out_coff", C.c_int),
+                ("bf16", C.c_int), ("hi2", C.c_void_p), ("lo2", C.c_void_p), ("bn", BnFinalize)]
 
 
 class BnBwd(C.Structure):

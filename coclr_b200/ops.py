@@ -53,7 +53,8 @@ def split_into(x, planes, coff=0, Cc=None, scale=None, shift=None, relu=False, o
     M = x.numel() // x.shape[-1]
     p = L.Split(L.dptr(x), x.shape[-1], coff, Cc, M, L.dptr(scale), L.dptr(shift), int(bool(relu)),
                 L.dptr(planes.hi), L.dptr(planes.lo), planes.ld, out_coff, planes.bf16,
-                L.dptr(twin.hi) if twin is not None else None, L.dptr(twin.lo) if twin is not None else None)
+                L.dptr(twin.hi) if twin is not None else None, L.dptr(twin.lo) if twin is not None else None,
+                L.BnFinalize())
     L.check(L.load().coclr_affine_split(C.byref(p), L.num_sms(), L.stream_ptr()), "coclr_affine_split")
     return planes
 

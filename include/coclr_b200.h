@@ -105,30 +105,10 @@ typedef struct {
 } coclr_pack_t;
 int coclr_pack_weights(const coclr_pack_t* p, coclr_stream_t stream);
 
-/* ---- BatchNorm-apply + ReLU + precision split --------------------------------------------------
- * hi/lo[m, out_coff + c] = split( relu?( scale[c] * x[m, coff + c] + shift[c] ) ); scale == NULL: identity.
- * The elementwise half of nn.BatchNorm3d + nn.ReLU (backbone/s3dg.py:16-17,24-27), one pass, producing the
- * operand planes every consumer (conv / pool / avg-pool) reads. */
-typedef struct {
-  const float* x;
-  int ld, coff, C; /* C multiple of 4 */
-  long M;
-  const float* scale;
-  const float* shift;
-  int relu;
-  void* hi;
-  void* lo; /* may be NULL */
-  int out_ld, out_coff;
-  int bf16;
-  void* hi2; /* optional bf16 twin of the planes (same out_ld / out_coff) for the weight-gradient GEMM, whose */
-  void* lo2; /* two operands must share one 16-bit format (tcgen05 kind::f16); NULL to skip */
-} coclr_split_t;
-int coclr_affine_split(const coclr_split_t* p, int num_sms, coclr_stream_t stream);
-
 /* ---- BatchNorm3d statistics -> affine (train mode; backbone/s3dg.py:16,46-47) ------------------
- * per-channel sums written by coclr_conv_igemm -> (scale, shift) for coclr_affine_split, saved (mean, rstd)
- * for backward, running-stat momentum update (unbiased variance).
- * training == 0: scale/shift from the running statistics (eval-mode BN, main_coclr.py:363). */
+ * per-channel sums written by coclr_conv_igemm -> (scale, shift), saved (mean, rstd) for backward, running-stat
+ * momentum update (unbiased variance).  training == 0: scale/shift from the running statistics (eval-mode BN,
+ * main_coclr.py:363).  Stand-alone launch (coclr_bn_finalize) or fused into coclr_affine_split. */
 typedef struct {
   const double* sum;
   const double* sumsq;
@@ -146,6 +126,31 @@ typedef struct {
   int C;
 } coclr_bn_finalize_t;
 int coclr_bn_finalize(const coclr_bn_finalize_t* p, coclr_stream_t stream);
+
+/* ---- BatchNorm-apply + ReLU + precision split --------------------------------------------------
+ * hi/lo[m, out_coff + c] = split( relu?( scale[c] * x[m, coff + c] + shift[c] ) ); scale == NULL: identity.
+ * The elementwise half of nn.BatchNorm3d + nn.ReLU (backbone/s3dg.py:16-17,24-27), one pass, producing the
+ * operand planes every consumer (conv / pool / avg-pool) reads. */
+typedef struct {
+  const float* x;
+  int ld, coff, C; /* C multiple of 4 */
+  long M;
+  const float* scale;
+  const float* shift;
+  int relu;
+  void* hi;
+  void* lo; /* may be NULL */
+  int out_ld, out_coff;
+  int bf16;
+  void* hi2; /* optional bf16 twin of the planes (same out_ld / out_coff) for the weight-gradient GEMM, whose */
+  void* lo2; /* two operands must share one 16-bit format (tcgen05 kind::f16); NULL to skip */
+  /* optional fused BatchNorm finalize (bn.scale != NULL): scale/shift are derived in-kernel from the statistics
+   * (bn.training) or the running stats, written to bn.scale/bn.shift/bn.save_* and the running stats are updated
+   * by one block -- saves the separate coclr_bn_finalize launch; `scale`/`shift` above are then ignored */
+  coclr_bn_finalize_t bn;
+} coclr_split_t;
+int coclr_affine_split(const coclr_split_t* p, int num_sms, coclr_stream_t stream);
+
 
 /* backward of BatchNorm+ReLU: dA (grad w.r.t. relu(bn(y)), fp32) -> dY (grad w.r.t. y) written as bf16
  * hi/lo planes for the dgrad / wgrad kernels; also dgamma / dbeta (accumulated).  Replaces

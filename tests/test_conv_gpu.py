@@ -242,3 +242,37 @@ def test_maxpool_fwd_bwd(k, s, p, diag):
     e = _rel(gdx, gref)
     diag["pool/%s" % (str(k) + str(s))] = e
     assert e < 1e-6
+
+
+@pytest.mark.parametrize("training", [1, 0])
+def test_fused_bn_finalize_apply_split(training, diag):
+    """coclr_affine_split with the BatchNorm finalize fused in, against F.batch_norm + relu (train and eval mode,
+    running-stat update included) -- nn.BatchNorm3d semantics of backbone/s3dg.py:16."""
+    import ctypes as C
+    from coclr_b200 import ops, lib as L
+    g = torch.Generator(device="cuda").manual_seed(21)
+    B, Cc, T, H, W = 2, 48, 3, 6, 5
+    x = torch.randn(B, Cc, T, H, W, device="cuda", generator=g) * 2 + 0.5
+    gamma = torch.rand(Cc, device="cuda", generator=g) + 0.5
+    beta = torch.randn(Cc, device="cuda", generator=g)
+    rm = torch.randn(Cc, device="cuda", generator=g) * 0.1
+    rv = torch.rand(Cc, device="cuda", generator=g) + 0.5
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    ref = torch.relu(F.batch_norm(x, rm_ref, rv_ref, gamma, beta, bool(training), 0.1, 1e-5)).permute(0, 2, 3, 4, 1)
+    rows = _rows(x)
+    M = rows.numel() // Cc
+    xs = rows.double().reshape(M, Cc)
+    ssum, ssq = xs.sum(0).contiguous(), (xs * xs).sum(0).contiguous()
+    scale, shift, mean, rstd = (torch.zeros(Cc, device="cuda") for _ in range(4))
+    pl = ops.Planes((B, T, H, W, Cc), 0, "cuda")
+    bn = L.BnFinalize(L.dptr(ssum), L.dptr(ssq), M, L.dptr(gamma), L.dptr(beta), L.dptr(rm), L.dptr(rv), 0.1, 1e-5,
+                      training, L.dptr(scale), L.dptr(shift), L.dptr(mean), L.dptr(rstd), Cc)
+    sp = L.Split(L.dptr(rows), Cc, 0, Cc, M, None, None, 1, L.dptr(pl.hi), L.dptr(pl.lo), Cc, 0, 0, None, None, bn)
+    L.check(L.load().coclr_affine_split(C.byref(sp), L.num_sms(), L.stream_ptr()), "coclr_affine_split")
+    torch.cuda.synchronize()
+    e = _rel(pl.value(), ref)
+    diag["fused_bn/train%d" % training] = e
+    assert e < 5e-6
+    assert _rel(rm, rm_ref) < 1e-6 and _rel(rv, rv_ref) < 1e-6
+    if training:
+        assert _rel(mean, xs.mean(0)) < 1e-6

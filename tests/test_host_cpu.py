@@ -115,12 +115,12 @@ def test_launch_plans_build_on_cpu_dry_run():
         names = [fn.__name__ for fn, _ in p.fwd]
         assert names.count("coclr_conv_igemm") == 77 + 2
         assert names.count("coclr_maxpool_fwd") == 13
-        assert names.count("coclr_bn_finalize") == 77 - 9 * 3   # one finalize per tensor; concat tensors hold 4 BNs
+        assert names.count("coclr_affine_split") == (77 - 9 * 3) + 2   # one fused BN-finalize+apply+split per tensor (concat tensors hold 4 BNs) + 2 head splits
         bn = [fn.__name__ for fn, _ in p.bwd]
         assert bn.count("coclr_conv_wgrad") == 77 + 2
         assert bn.count("coclr_conv_igemm") == 76 + 2           # no dgrad for the RGB stem conv
         assert bn.count("coclr_maxpool_bwd") == 13
-        assert bn.count("coclr_bn_bwd") == names.count("coclr_bn_finalize")
+        assert bn.count("coclr_bn_bwd") == 77 - 9 * 3
         # inference plan has no gradient buffers
         p2 = eng.plan(2, 8, 64, 64, True, False)
         assert not p2.bwd and all(a.grad is None for a in p2.acts.values())
