@@ -113,60 +113,57 @@ __global__ void __launch_bounds__(256) affine_split_kernel(const coclr_split_t P
 // ------------------------------------------------------------------------------------------------
 static constexpr int kColThreads = 256;
 
-// BatchNorm finalize fused with apply + ReLU + split: every thread derives (scale, shift) of its own 4 channels
-// from the statistics; block 0 also publishes them (backward needs scale/shift/mean/rstd) and updates the running
-// statistics.  Same column mapping as the BN backward kernels.
+// BatchNorm finalize fused with apply + ReLU + split: every block derives (scale, shift) of all channels into
+// shared memory from the statistics (cheap: C <= 1024), block 0 also publishes them (backward needs
+// scale/shift/mean/rstd) and updates the running statistics; then the same flat, fully coalesced pass as
+// affine_split_kernel.
 template <bool kBf16>
-__global__ void __launch_bounds__(kColThreads) bn_apply_split_kernel(const coclr_split_t P) {
-  const int C4 = P.C >> 2;
-  const int A = (kColThreads / C4) * C4;
-  const int R = A / C4;
-  const int t = threadIdx.x;
-  if (t >= A) return;
-  const int cg = t % C4, rs = t / C4;
-  const int c = cg * 4;
+__global__ void __launch_bounds__(256) bn_apply_split_kernel(const coclr_split_t P) {
+  __shared__ float s_sc[1024], s_sh[1024];
   const coclr_bn_finalize_t& F = P.bn;
-  float sc[4], sh[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int c = threadIdx.x; c < P.C; c += blockDim.x) {
     float mean, var;
     if (F.training) {
       const double n = (double)F.count;
-      const double m = F.sum[c + j] / n;
-      double v = F.sumsq[c + j] / n - m * m;
+      const double m = F.sum[c] / n;
+      double v = F.sumsq[c] / n - m * m;
       if (v < 0.0) v = 0.0;
       mean = (float)m;
       var = (float)v;
-      if (blockIdx.x == 0 && rs == 0) {
+      if (blockIdx.x == 0) {
         const float unbiased = (float)(F.count > 1 ? v * n / (n - 1.0) : v);
-        F.running_mean[c + j] = (1.f - F.momentum) * F.running_mean[c + j] + F.momentum * mean;
-        F.running_var[c + j] = (1.f - F.momentum) * F.running_var[c + j] + F.momentum * unbiased;
+        F.running_mean[c] = (1.f - F.momentum) * F.running_mean[c] + F.momentum * mean;
+        F.running_var[c] = (1.f - F.momentum) * F.running_var[c] + F.momentum * unbiased;
       }
     } else {
-      mean = F.running_mean[c + j];
-      var = F.running_var[c + j];
+      mean = F.running_mean[c];
+      var = F.running_var[c];
     }
     const float rstd = 1.f / sqrtf(var + F.eps);
-    sc[j] = F.gamma[c + j] * rstd;
-    sh[j] = F.beta[c + j] - mean * sc[j];
-    if (blockIdx.x == 0 && rs == 0) {
-      F.scale[c + j] = sc[j];
-      F.shift[c + j] = sh[j];
-      if (F.save_mean) F.save_mean[c + j] = mean;
-      if (F.save_rstd) F.save_rstd[c + j] = rstd;
+    const float sc = F.gamma[c] * rstd;
+    const float sh = F.beta[c] - mean * sc;
+    s_sc[c] = sc;
+    s_sh[c] = sh;
+    if (blockIdx.x == 0) {
+      F.scale[c] = sc;
+      F.shift[c] = sh;
+      if (F.save_mean) F.save_mean[c] = mean;
+      if (F.save_rstd) F.save_rstd[c] = rstd;
     }
   }
+  __syncthreads();
+  const int C4 = P.C >> 2;
+  const long total = P.M * C4;
   uint16_t* hi = reinterpret_cast<uint16_t*>(P.hi);
   uint16_t* lo = reinterpret_cast<uint16_t*>(P.lo);
-  const long rows_per = ((long)P.M + gridDim.x - 1) / gridDim.x;
-  const long r_begin = (long)blockIdx.x * rows_per;
-  const long r_end = min((long)P.M, r_begin + rows_per);
-  for (long r = r_begin + rs; r < r_end; r += R) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / C4;
+    const int c = (int)(i - r * C4) * 4;
     float4 v = ld4(P.x + r * P.ld + P.coff + c);
-    v.x = fmaf(v.x, sc[0], sh[0]);
-    v.y = fmaf(v.y, sc[1], sh[1]);
-    v.z = fmaf(v.z, sc[2], sh[2]);
-    v.w = fmaf(v.w, sc[3], sh[3]);
+    v.x = fmaf(v.x, s_sc[c + 0], s_sh[c + 0]);
+    v.y = fmaf(v.y, s_sc[c + 1], s_sh[c + 1]);
+    v.z = fmaf(v.z, s_sc[c + 2], s_sh[c + 2]);
+    v.w = fmaf(v.w, s_sc[c + 3], s_sh[c + 3]);
     if (P.relu) {
       v.x = fmaxf(v.x, 0.f);
       v.y = fmaxf(v.y, 0.f);
@@ -360,6 +357,98 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const coclr_pool_t P) 
       st_pair4<true>(reinterpret_cast<uint16_t*>(P.y2_hi), reinterpret_cast<uint16_t*>(P.y2_lo), oo,
                      make_float4(best[0], best[1], best[2], best[3]));
     if (P.idx) *reinterpret_cast<uchar4*>(P.idx + o * P.C + c) = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
+  }
+}
+
+// 3x3x3 / stride 1 / pad 1 (the Inception branch-3 pool, 18 of the 26 pool launches of a step): each thread
+// produces 4 consecutive outputs along x for 4 channels and shares the loaded columns between them: first the
+// maximum over the 9 (t,y) taps of each of the 6 input columns, then 3 columns per output.  Ties resolve to the
+// first tap in (t,y,x) scan order like nn.MaxPool3d.
+__global__ void __launch_bounds__(256) maxpool333_fwd_kernel(const coclr_pool_t P) {
+  const int C4 = P.C >> 2;
+  const int XG = P.Wo >> 2;  // Wo % 4 == 0 checked by the launcher
+  const long total = (long)P.B * P.To * P.Ho * XG * C4;
+  const uint16_t* xh = reinterpret_cast<const uint16_t*>(P.x_hi);
+  const uint16_t* xl = reinterpret_cast<const uint16_t*>(P.x_lo);
+  uint16_t* yh = reinterpret_cast<uint16_t*>(P.y_hi);
+  uint16_t* yl = reinterpret_cast<uint16_t*>(P.y_lo);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % C4);
+    long r = i / C4;
+    const int xg = (int)(r % XG); r /= XG;
+    const int yo = (int)(r % P.Ho); r /= P.Ho;
+    const int to = (int)(r % P.To);
+    const int b = (int)(r / P.To);
+    const int c = cg * 4;
+    const int x0 = xg * 4 - 1;  // first input column
+    float cv[6][4];
+    uint16_t ch[6][4], cl[6][4];
+    unsigned char cab[6][4];
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { cv[j][k] = -INFINITY; ch[j][k] = 0xfc00; cl[j][k] = 0; cab[j][k] = 0; }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int ti = to - 1 + a;
+      if ((unsigned)ti >= (unsigned)P.Ti) continue;
+#pragma unroll
+      for (int bb = 0; bb < 3; ++bb) {
+        const int yi = yo - 1 + bb;
+        if ((unsigned)yi >= (unsigned)P.Hi) continue;
+        const size_t rowoff = (((size_t)b * P.Ti + ti) * P.Hi + yi) * P.Wi;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int xi = x0 + j;
+          if ((unsigned)xi >= (unsigned)P.Wi) continue;
+          const size_t off = (rowoff + xi) * P.ldx + P.x_coff + c;
+          const uint2 h = *reinterpret_cast<const uint2*>(xh + off);
+          uint2 l = make_uint2(0u, 0u);
+          if (xl != nullptr) l = *reinterpret_cast<const uint2*>(xl + off);
+          const uint16_t hh[4] = {(uint16_t)(h.x & 0xffff), (uint16_t)(h.x >> 16), (uint16_t)(h.y & 0xffff),
+                                  (uint16_t)(h.y >> 16)};
+          const uint16_t ll[4] = {(uint16_t)(l.x & 0xffff), (uint16_t)(l.x >> 16), (uint16_t)(l.y & 0xffff),
+                                  (uint16_t)(l.y >> 16)};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float v = h2f(hh[k]) + h2f(ll[k]);
+            if (v > cv[j][k]) { cv[j][k] = v; ch[j][k] = hh[k]; cl[j][k] = ll[k]; cab[j][k] = (unsigned char)(a * 3 + bb); }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o4 = 0; o4 < 4; ++o4) {
+      float best[4];
+      uint16_t bh[4], bl[4];
+      unsigned char bab[4], bcc[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { best[k] = cv[o4][k]; bh[k] = ch[o4][k]; bl[k] = cl[o4][k]; bab[k] = cab[o4][k]; bcc[k] = 0; }
+#pragma unroll
+      for (int cc = 1; cc < 3; ++cc)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float v = cv[o4 + cc][k];
+          const unsigned char ab = cab[o4 + cc][k];
+          if (v > best[k] || (v == best[k] && ab < bab[k])) {   // earlier (t,y) wins a tie; same (t,y): smaller x
+            best[k] = v; bh[k] = ch[o4 + cc][k]; bl[k] = cl[o4 + cc][k]; bab[k] = ab; bcc[k] = (unsigned char)cc;
+          }
+        }
+      const size_t o = ((((size_t)b * P.To + to) * P.Ho + yo) * P.Wo + xg * 4 + o4);
+      const size_t oo = o * P.ldy + P.y_coff + c;
+      *reinterpret_cast<uint2*>(yh + oo) =
+          make_uint2((uint32_t)bh[0] | ((uint32_t)bh[1] << 16), (uint32_t)bh[2] | ((uint32_t)bh[3] << 16));
+      if (yl != nullptr)
+        *reinterpret_cast<uint2*>(yl + oo) =
+            make_uint2((uint32_t)bl[0] | ((uint32_t)bl[1] << 16), (uint32_t)bl[2] | ((uint32_t)bl[3] << 16));
+      if (P.y2_hi != nullptr)
+        st_pair4<true>(reinterpret_cast<uint16_t*>(P.y2_hi), reinterpret_cast<uint16_t*>(P.y2_lo), oo,
+                       make_float4(best[0], best[1], best[2], best[3]));
+      if (P.idx)
+        *reinterpret_cast<uchar4*>(P.idx + o * P.C + c) =
+            make_uchar4((unsigned char)(bab[0] * 3 + bcc[0]), (unsigned char)(bab[1] * 3 + bcc[1]),
+                        (unsigned char)(bab[2] * 3 + bcc[2]), (unsigned char)(bab[3] * 3 + bcc[3]));
+    }
   }
 }
 
@@ -594,14 +683,11 @@ extern "C" int coclr_affine_split(const coclr_split_t* p, int num_sms, coclr_str
     const coclr_bn_finalize_t& f = p->bn;
     if (!f.shift || !f.gamma || !f.beta || !f.running_mean || !f.running_var || p->C > 1024) return COCLR_E_ARG;
     if (f.training && (!f.sum || !f.sumsq || f.count <= 0)) return COCLR_E_ARG;
-    const int R = kColThreads / (p->C / 4);
-    long slabs = (p->M + (long)R * 16 - 1) / ((long)R * 16);
-    int grid = (int)(slabs < (long)num_sms * 8 ? slabs : (long)num_sms * 8);
-    if (grid < 1) grid = 1;
+    const int grid = grid_for(total, 256, num_sms * 16);
     if (p->bf16)
-      bn_apply_split_kernel<true><<<grid, kColThreads, 0, (cudaStream_t)stream>>>(*p);
+      bn_apply_split_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
     else
-      bn_apply_split_kernel<false><<<grid, kColThreads, 0, (cudaStream_t)stream>>>(*p);
+      bn_apply_split_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
     return LAUNCH_OK();
   }
   const int grid = grid_for(total, 256, num_sms * 16);
@@ -662,6 +748,12 @@ extern "C" int coclr_maxpool_fwd(const coclr_pool_t* p, coclr_stream_t stream) {
     return COCLR_E_ARG;
   if (p->g.kt * p->g.kh * p->g.kw > 255) return COCLR_E_ARG;
   const long total = (long)p->B * p->To * p->Ho * p->Wo * (p->C / 4);
+  const coclr_geom_t& g = p->g;
+  if (g.kt == 3 && g.kh == 3 && g.kw == 3 && g.st == 1 && g.sh == 1 && g.sw == 1 && g.pt == 1 && g.ph == 1 &&
+      g.pw == 1 && (p->Wo % 4) == 0 && p->Wo == p->Wi && p->Ho == p->Hi && p->To == p->Ti) {
+    maxpool333_fwd_kernel<<<grid_for(total / 4, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(*p);
+    return LAUNCH_OK();
+  }
   launch_pool<false>(*p, total, (cudaStream_t)stream);
   return LAUNCH_OK();
 }

@@ -211,13 +211,16 @@ POOLS = [((1, 3, 3), (1, 2, 2), (0, 1, 1)), ((3, 3, 3), (1, 1, 1), (1, 1, 1)), (
          ((2, 2, 2), (2, 2, 2), (0, 0, 0)), ((1, 2, 3), (1, 1, 2), (0, 1, 1))]
 
 
+@pytest.mark.parametrize("dims", [(6, 9, 10), (4, 8, 12)], ids=["ragged", "x4"])
 @pytest.mark.parametrize("k,s,p", POOLS, ids=["133s2", "333s1", "333s2", "222s2", "generic"])
-def test_maxpool_fwd_bwd(k, s, p, diag):
+def test_maxpool_fwd_bwd(k, s, p, dims, diag):
     import ctypes as C
     from coclr_b200 import ops, lib as L
     g = torch.Generator(device="cuda").manual_seed(13)
-    B, Cc, T, H, W = 2, 24, 6, 9, 10
+    B, Cc = 2, 24
+    T, H, W = dims
     x = torch.randn(B, Cc, T, H, W, device="cuda", generator=g)
+    x = torch.relu(x)                     # post-ReLU inputs as in the network: many exact ties at 0
     pl, Cp, coff = _planes_of(ops, x, 0)
     xv = pl.value()[..., coff:coff + Cc].permute(0, 4, 1, 2, 3).double().requires_grad_(True)   # exact plane values
     ref = F.max_pool3d(xv, k, s, p)
