@@ -528,19 +528,39 @@ class EncoderEngine:
             self.plans[key] = p
         return p
 
-    def _run(self, oplist):
-        stream = L.stream_ptr()
+    overlap_wgrad = True  # run the weight-gradient GEMMs on a side stream, concurrently with the dgrad chain
+
+    def _run(self, oplist, side_fn=None):
+        """Launch the list on the current stream. Ops whose function is `side_fn` (the weight-gradient GEMMs, which
+        nothing downstream in the list depends on) go to a side stream that waits for the producer of their inputs
+        and is joined at the end: small layers leave most SMs idle, so the two chains overlap."""
+        main = torch.cuda.current_stream()
+        stream = C.c_void_p(main.cuda_stream)
         prof = EncoderEngine.profile
+        use_side = side_fn is not None and prof is None and EncoderEngine.overlap_wgrad
+        if use_side:
+            if getattr(self, "_side", None) is None:
+                self._side = torch.cuda.Stream()
+            side = self._side
+            side_ptr = C.c_void_p(side.cuda_stream)
+            side_used = False
         for fn, args in oplist:
-            if prof is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            rc = fn(*args, stream)
-            if prof is not None:
-                e1.record()
-                prof.append((fn.__name__, args, e0, e1))
+            if use_side and fn is side_fn:
+                side.wait_stream(main)           # inputs (dY planes) were produced by ops already queued on main
+                rc = fn(*args, side_ptr)
+                side_used = True
+            else:
+                if prof is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                rc = fn(*args, stream)
+                if prof is not None:
+                    e1.record()
+                    prof.append((fn.__name__, args, e0, e1))
             if rc != 0:
                 raise L.CoclrError("%s failed with code %d" % (fn.__name__, rc))
+        if use_side and side_used:
+            main.wait_stream(side)
         L.LAUNCHES += sum(L.KERNELS_PER_CALL.get(fn.__name__, 1) for fn, _ in oplist)
 
     def forward(self, x, training=True, with_backward=False, repack=True, batch_index=None, batch=None):
@@ -573,7 +593,7 @@ class EncoderEngine:
     def backward(self, p, dq):
         """dq: gradient w.r.t. the normalised features [B, dim]; accumulates into store.grad."""
         p.dq.copy_(dq)
-        self._run(p.bwd)
+        self._run(p.bwd, side_fn=L.load().coclr_conv_wgrad)
 
     def backbone_output_ncdhw(self, p):
         return p.backbone_out.pl.value().permute(0, 4, 1, 2, 3).contiguous()

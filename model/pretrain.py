@@ -46,6 +46,7 @@ class InfoNCE(nn.Module):
         self.register_buffer("queue", nn.functional.normalize(torch.randn(dim, K), dim=0))
         self.register_buffer("queue_ptr", torch.zeros(1, dtype=torch.long))
         self._ptr_host = None
+        self._side_stream = None
 
     # -- queue pointer mirror ---------------------------------------------------------------------
     def _load_from_state_dict(self, *args, **kwargs):
@@ -97,12 +98,20 @@ class InfoNCE(nn.Module):
         (B, N, *_) = block.shape
         assert N == 2                                                                 # pretrain.py:148
         x1, x2 = block[:, 0], block[:, 1]          # views; the .contiguous() copies are folded into packing
-        q = self.encoder_q.encode(x1)
-        in_train_mode = q.requires_grad                                               # :157
-        with torch.no_grad():
+        in_train_mode = torch.is_grad_enabled() and any(p.requires_grad for p in self.encoder_q.parameters())  # :157
+        # the key branch (EMA -> shuffle -> encoder_k) does not depend on the query forward: run it on a side stream
+        # so that the many small layers of the two encoders fill the SMs together
+        main = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream()
+        side = self._side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side), torch.no_grad():
             if in_train_mode:
                 self._momentum_update_key_encoder()                                   # :161
             k, k_global = self._shuffled_keys(x2)
+        q = self.encoder_q.encode(x1)                                                 # :153-155
+        main.wait_stream(side)
         return q, k, k_global, in_train_mode
 
     def forward(self, block):
