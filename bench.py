@@ -163,13 +163,16 @@ def wgrad_flops(wg):
 
 def kernel_breakdown(run_step):
     from coclr_b200.engine import EncoderEngine
+    from model.pretrain import InfoNCE
     EncoderEngine.profile = []
+    InfoNCE.overlap_key_branch = False      # per-kernel durations are only meaningful without stream overlap
     try:
         run_step()
         torch.cuda.synchronize()
         prof = EncoderEngine.profile
     finally:
         EncoderEngine.profile = None
+        InfoNCE.overlap_key_branch = True
     table = {}
     for name, a, e0, e1 in prof:
         ms = e0.elapsed_time(e1)

@@ -60,11 +60,31 @@ def _conv_out(d, k, s, p):
     return (d + 2 * p - k) // s + 1
 
 
+FORK, JOIN = 1, 2
+
+
+class _LaneList(list):
+    """items list that records the current lane / pending flag of the graph builder for every appended item."""
+
+    def __init__(self, graph):
+        super().__init__()
+        self.graph = graph
+
+    def append(self, item):
+        g = self.graph
+        g.item_lane.append(g.cur_lane)
+        g.item_flag.append(g.next_flag)
+        g.next_flag = 0
+        super().append(item)
+
+
 class Graph:
     """Shape-independent description of the encoder: tensors, convs, pools in forward order."""
 
     def __init__(self, stages, first_channel=3, head_dim=None, feature_size=S3D_FEATURE_SIZE, bb_prefix=""):
-        self.tensors, self.items = [], []   # items: ("conv", ConvSpec) | ("pool", PoolSpec) | ("bn", TensorSpec)
+        self.tensors, self.items = [], _LaneList(self)   # items: ("conv", ConvSpec) | ("pool", PoolSpec) | ("bn", TensorSpec)
+        self.item_lane, self.item_flag = [], []   # per item: stream lane (Inception branches run concurrently) and FORK/JOIN
+        self.cur_lane, self.next_flag = 0, 0
         self.first_channel = first_channel
         self.head_dim, self.feature_size = head_dim, feature_size
         pre = bb_prefix
@@ -140,21 +160,26 @@ class Graph:
         o0, o1a, o1b, o2a, o2b, o3b = planes
         cat = self._tensor(name, o0 + o1b + o2b + o3b, self._same(x))
         one = ((1, 1, 1), (1, 1, 1), (0, 0, 0))
+        self.cur_lane, self.next_flag = 0, FORK     # the four branches only share the (read-only) input planes
         self._conv(name + ".branch0.0.conv", x, cat, 0, cin, o0, *one)
         cat.bn_members.append((name + ".branch0.0.bn", 0, o0))
+        self.cur_lane = 1
         t1 = self._tensor(name + ".b1a", o1a, self._same(x))
         self._conv(name + ".branch1.0.conv", x, t1, 0, cin, o1a, *one)
         t1.bn_members.append((name + ".branch1.0.bn", 0, o1a))
         self.items.append(("bn", t1))
         self._st(name + ".branch1.1", t1, cat, o0, o1a, o1b, 3, 1, 1, 1)
+        self.cur_lane = 2
         t2 = self._tensor(name + ".b2a", o2a, self._same(x))
         self._conv(name + ".branch2.0.conv", x, t2, 0, cin, o2a, *one)
         t2.bn_members.append((name + ".branch2.0.bn", 0, o2a))
         self.items.append(("bn", t2))
         self._st(name + ".branch2.1", t2, cat, o0 + o1b, o2a, o2b, 3, 1, 1, 1)
+        self.cur_lane = 3
         tp = self._pool(name + ".branch3.0", x, (3, 3, 3), (1, 1, 1), (1, 1, 1))
         self._conv(name + ".branch3.1.conv", tp, cat, o0 + o1b + o2b, cin, o3b, *one)
         cat.bn_members.append((name + ".branch3.1.bn", o0 + o1b + o2b, o3b))
+        self.cur_lane, self.next_flag = 0, JOIN
         self.items.append(("bn", cat))
         return cat
 
@@ -267,6 +292,7 @@ class Plan:
         lib = L.load()
         self.keep = []          # keeps ctypes structs / tensors alive
         self.fwd, self.bwd = [], []
+        self.fwd_lane = {}      # index into self.fwd -> (lane, FORK/JOIN flag)
         nsm = L.num_sms(dev)
         fnp, fbf, bnp = PRECISIONS[eng.precision]
         # ---- activations ----
@@ -323,7 +349,8 @@ class Plan:
             return (lib.coclr_affine_split, (C.byref(sp), nsm))
 
         # ---- forward ----
-        for kind, it in g.items:
+        for item_i, (kind, it) in enumerate(g.items):
+            n_before = len(self.fwd)
             if kind == "conv":
                 sa, da = acts[it.src.index], acts[it.dst.index]
                 geom = ops.Geometry(it.k, it.s, it.p)
@@ -358,6 +385,8 @@ class Plan:
                                   L.dptr(a.mean), L.dptr(a.rstd), it.C)
                 # BatchNorm finalize is fused into the apply+split launch
                 self.fwd.append(split_op(a.data, a.pl, a.M, it.C, None, None, it.relu, a.plw, bn=bf))
+            for j in range(n_before, len(self.fwd)):     # tag the launches of this item with its lane / fork / join
+                self.fwd_lane[j] = (g.item_lane[item_i], g.item_flag[item_i] if j == n_before else 0)
         # ---- head ----
         out = acts[g.backbone_out.index]
         self.backbone_out = out
@@ -530,6 +559,36 @@ class EncoderEngine:
 
     overlap_wgrad = True  # run the weight-gradient GEMMs on a side stream, concurrently with the dgrad chain
 
+    overlap_branches = True  # run the four Inception branches of a block on four streams (forward)
+
+    def _run_lanes(self, oplist, lanes):
+        """Forward launch list with fork/join: ops tagged lane 1..3 run on side streams that wait for the fork
+        point (an event on the main stream recorded before the block's first op); the JOIN op first waits for them."""
+        main = torch.cuda.current_stream()
+        if getattr(self, "_lane_streams", None) is None:
+            self._lane_streams = [None] + [torch.cuda.Stream() for _ in range(3)]
+        ptrs = [C.c_void_p(main.cuda_stream)] + [C.c_void_p(s.cuda_stream) for s in self._lane_streams[1:]]
+        fork_ev, active = None, set()
+        for i, (fn, args) in enumerate(oplist):
+            lane, flag = lanes.get(i, (0, 0))
+            if flag == FORK:
+                fork_ev = torch.cuda.Event()
+                fork_ev.record(main)
+                active = set()
+            elif flag == JOIN:
+                for ln in active:
+                    main.wait_stream(self._lane_streams[ln])
+                active = set()
+            if lane != 0 and lane not in active:
+                self._lane_streams[lane].wait_event(fork_ev)
+                active.add(lane)
+            rc = fn(*args, ptrs[lane])
+            if rc != 0:
+                raise L.CoclrError("%s failed with code %d" % (fn.__name__, rc))
+        for ln in active:
+            main.wait_stream(self._lane_streams[ln])
+        L.LAUNCHES += sum(L.KERNELS_PER_CALL.get(fn.__name__, 1) for fn, _ in oplist)
+
     def _run(self, oplist, side_fn=None):
         """Launch the list on the current stream. Ops whose function is `side_fn` (the weight-gradient GEMMs, which
         nothing downstream in the list depends on) go to a side stream that waits for the producer of their inputs
@@ -587,7 +646,10 @@ class EncoderEngine:
                                      L.dptr(p.input.pl.lo), L.dptr(tw.hi) if tw else None,
                                      L.dptr(tw.lo) if tw else None, B, T * H * W, L.dptr(batch_index), L.stream_ptr()),
                 "coclr_pack_input")
-        self._run(p.fwd)
+        if EncoderEngine.overlap_branches and EncoderEngine.profile is None:
+            self._run_lanes(p.fwd, p.fwd_lane)
+        else:
+            self._run(p.fwd)
         return p
 
     def backward(self, p, dq):

@@ -27,6 +27,8 @@ from coclr_b200.moco import concat_all_gather  # noqa: F401  (re-exported: refer
 class InfoNCE(nn.Module):
     """MoCo for video (reference model/pretrain.py:28-190)."""
 
+    overlap_key_branch = True   # run EMA + shuffle + encoder_k on a side stream next to the query forward
+
     def __init__(self, network='s3d', dim=128, K=2048, m=0.999, T=0.07, precision="parity"):
         super().__init__()
         self.dim, self.K, self.m, self.T = dim, K, m, T
@@ -97,6 +99,8 @@ class InfoNCE(nn.Module):
     def _qk(self, block):
         (B, N, *_) = block.shape
         assert N == 2                                                                 # pretrain.py:148
+        if not block.is_cuda:
+            raise moco.L.CoclrError("coclr_b200 modules run on CUDA (sm_100a) only; there is no CPU path")
         x1, x2 = block[:, 0], block[:, 1]          # views; the .contiguous() copies are folded into packing
         in_train_mode = torch.is_grad_enabled() and any(p.requires_grad for p in self.encoder_q.parameters())  # :157
         # the key branch (EMA -> shuffle -> encoder_k) does not depend on the query forward: run it on a side stream
@@ -104,7 +108,7 @@ class InfoNCE(nn.Module):
         main = torch.cuda.current_stream()
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream()
-        side = self._side_stream
+        side = self._side_stream if InfoNCE.overlap_key_branch else main
         side.wait_stream(main)
         with torch.cuda.stream(side), torch.no_grad():
             if in_train_mode:
