@@ -237,8 +237,10 @@ def main():
     l0 = L.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host = time.perf_counter()
     for i in range(args.steps):
         train_step(dev_blocks[i % 2])
+    host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps   # host time to ENQUEUE one step (no sync inside)
     e1.record()
     barrier()
     launches = (L.LAUNCHES - l0) // max(1, args.steps)
@@ -361,7 +363,7 @@ def main():
                                        % (B, T),
                            "global_batch": B * world, "parallelism": "dp%d" % world, "precision": args.precision,
                            "l2": "two alternating 403 MB input blocks per rank (> 126 MB L2)",
-                           "pairs_per_s": value / 2, "final_loss": final_loss,
+                           "pairs_per_s": value / 2, "final_loss": final_loss, "host_enqueue_ms_per_step": host_ms,
                            "algorithmic_tflops": value / 2 * GFLOP_PER_PAIR / 1e3},
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline}

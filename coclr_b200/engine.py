@@ -12,6 +12,7 @@ gradient buffer).  Parameters live in ONE flat fp32 buffer per encoder (nn.Param
 EMA / Adam / all-reduce are single launches over it.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -293,6 +294,7 @@ class Plan:
         self.keep = []          # keeps ctypes structs / tensors alive
         self.fwd, self.bwd = [], []
         self.fwd_lane = {}      # index into self.fwd -> (lane, FORK/JOIN flag)
+        self.graphs = {}        # captured CUDA graphs of the launch lists
         nsm = L.num_sms(dev)
         fnp, fbf, bnp = PRECISIONS[eng.precision]
         # ---- activations ----
@@ -635,27 +637,55 @@ class EncoderEngine:
         if batch_index is not None:
             assert batch_index.dtype == torch.long and batch_index.is_cuda and batch_index.numel() == B
         p = self.plan(B, T, H, W, training, with_backward)
-        if repack:
-            self.pack_weights(backward=with_backward)
-        if training:
-            p.stats.zero_()
-            self.store.nbt += 1
         lib = L.load()
         tw = p.input.plw if (p.input.plw is not None and p.input.plw is not p.input.pl) else None
+        # the clip pointer / shuffle index change from call to call, so packing stays outside the captured graph
         L.check(lib.coclr_pack_input(L.dptr(x), x.stride(0), x.stride(1), Cin, L.dptr(p.input.pl.hi),
                                      L.dptr(p.input.pl.lo), L.dptr(tw.hi) if tw else None,
                                      L.dptr(tw.lo) if tw else None, B, T * H * W, L.dptr(batch_index), L.stream_ptr()),
                 "coclr_pack_input")
-        if EncoderEngine.overlap_branches and EncoderEngine.profile is None:
-            self._run_lanes(p.fwd, p.fwd_lane)
-        else:
-            self._run(p.fwd)
+
+        def body():
+            if repack:
+                self.pack_weights(backward=with_backward)
+            if training:
+                p.stats.zero_()
+                self.store.nbt += 1
+            if EncoderEngine.overlap_branches and EncoderEngine.profile is None:
+                self._run_lanes(p.fwd, p.fwd_lane)
+            else:
+                self._run(p.fwd)
+        self._graphed(p, "fwd" + ("_repack" if repack else ""), body)
         return p
+
+    use_graphs = os.environ.get("COCLR_GRAPHS", "1") != "0"
+
+    def _graphed(self, p, key, body):
+        """Every launch of `body` has fixed pointers and shapes: after one eager run (which also performs the
+        one-time cudaFuncSetAttribute calls) capture it -- stream forks/joins included -- into a CUDA graph and
+        replay that; the host then enqueues an encoder pass with one call instead of ~400."""
+        if not EncoderEngine.use_graphs or EncoderEngine.profile is not None:
+            body()
+            return
+        state = p.graphs.get(key)
+        if state is None:
+            body()
+            p.graphs[key] = "warm"
+        elif state == "warm":
+            g = torch.cuda.CUDAGraph()
+            before = L.LAUNCHES
+            with torch.cuda.graph(g):
+                body()
+            p.graphs[key] = (g, L.LAUNCHES - before)
+            g.replay()
+        else:
+            state[0].replay()
+            L.LAUNCHES += state[1]
 
     def backward(self, p, dq):
         """dq: gradient w.r.t. the normalised features [B, dim]; accumulates into store.grad."""
         p.dq.copy_(dq)
-        self._run(p.bwd, side_fn=L.load().coclr_conv_wgrad)
+        self._graphed(p, "bwd", lambda: self._run(p.bwd, side_fn=L.load().coclr_conv_wgrad))
 
     def backbone_output_ncdhw(self, p):
         return p.backbone_out.pl.value().permute(0, 4, 1, 2, 3).contiguous()
