@@ -364,7 +364,14 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const coclr_pool_t P) 
 // produces 4 consecutive outputs along x for 4 channels and shares the loaded columns between them: first the
 // maximum over the 9 (t,y) taps of each of the 6 input columns, then 3 columns per output.  Ties resolve to the
 // first tap in (t,y,x) scan order like nn.MaxPool3d.
-__global__ void __launch_bounds__(256) maxpool333_fwd_kernel(const coclr_pool_t P) {
+// order-preserving map of an fp16 bit pattern to an unsigned integer (and back): value order == integer order
+COCLR_DEVINL uint32_t f16_sortable(uint32_t h) { return (h & 0x8000u) ? (~h & 0xffffu) : (h | 0x8000u); }
+COCLR_DEVINL uint32_t f16_unsortable(uint32_t k) { return (k & 0x8000u) ? (k & 0x7fffu) : (~k & 0xffffu); }
+// (hi, lo) pair -> one 32-bit key whose integer order is the order of hi + lo (hi is the rounded value, so
+// pairs compare lexicographically)
+COCLR_DEVINL uint32_t pair_key(uint32_t hh, uint32_t ll) { return (f16_sortable(hh) << 16) | f16_sortable(ll); }
+
+__global__ void __launch_bounds__(256, 3) maxpool333_fwd_kernel(const coclr_pool_t P) {
   const int C4 = P.C >> 2;
   const int XG = P.Wo >> 2;  // Wo % 4 == 0 checked by the launcher
   const long total = (long)P.B * P.To * P.Ho * XG * C4;
@@ -381,13 +388,14 @@ __global__ void __launch_bounds__(256) maxpool333_fwd_kernel(const coclr_pool_t 
     const int b = (int)(r / P.To);
     const int c = cg * 4;
     const int x0 = xg * 4 - 1;  // first input column
-    float cv[6][4];
-    uint16_t ch[6][4], cl[6][4];
-    unsigned char cab[6][4];
+    uint32_t ck[6][4];          // best key of each column over the 9 (t,y) taps (0 = below every real key)
+    uint32_t cab[6];            // 4 x 8-bit (t,y) tap index of that best, one byte per channel
 #pragma unroll
-    for (int j = 0; j < 6; ++j)
+    for (int j = 0; j < 6; ++j) {
+      cab[j] = 0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { cv[j][k] = -INFINITY; ch[j][k] = 0xfc00; cl[j][k] = 0; cab[j][k] = 0; }
+      for (int k = 0; k < 4; ++k) ck[j][k] = 0;
+    }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const int ti = to - 1 + a;
@@ -396,6 +404,7 @@ __global__ void __launch_bounds__(256) maxpool333_fwd_kernel(const coclr_pool_t 
       for (int bb = 0; bb < 3; ++bb) {
         const int yi = yo - 1 + bb;
         if ((unsigned)yi >= (unsigned)P.Hi) continue;
+        const uint32_t ab = (uint32_t)(a * 3 + bb);
         const size_t rowoff = (((size_t)b * P.Ti + ti) * P.Hi + yi) * P.Wi;
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
@@ -405,45 +414,43 @@ __global__ void __launch_bounds__(256) maxpool333_fwd_kernel(const coclr_pool_t 
           const uint2 h = *reinterpret_cast<const uint2*>(xh + off);
           uint2 l = make_uint2(0u, 0u);
           if (xl != nullptr) l = *reinterpret_cast<const uint2*>(xl + off);
-          const uint16_t hh[4] = {(uint16_t)(h.x & 0xffff), (uint16_t)(h.x >> 16), (uint16_t)(h.y & 0xffff),
-                                  (uint16_t)(h.y >> 16)};
-          const uint16_t ll[4] = {(uint16_t)(l.x & 0xffff), (uint16_t)(l.x >> 16), (uint16_t)(l.y & 0xffff),
-                                  (uint16_t)(l.y >> 16)};
+          const uint32_t key[4] = {pair_key(h.x & 0xffffu, l.x & 0xffffu), pair_key(h.x >> 16, l.x >> 16),
+                                   pair_key(h.y & 0xffffu, l.y & 0xffffu), pair_key(h.y >> 16, l.y >> 16)};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float v = h2f(hh[k]) + h2f(ll[k]);
-            if (v > cv[j][k]) { cv[j][k] = v; ch[j][k] = hh[k]; cl[j][k] = ll[k]; cab[j][k] = (unsigned char)(a * 3 + bb); }
-          }
+          for (int k = 0; k < 4; ++k)
+            if (key[k] > ck[j][k]) {
+              ck[j][k] = key[k];
+              cab[j] = (cab[j] & ~(0xffu << (8 * k))) | (ab << (8 * k));
+            }
         }
       }
     }
 #pragma unroll
     for (int o4 = 0; o4 < 4; ++o4) {
-      float best[4];
-      uint16_t bh[4], bl[4];
-      unsigned char bab[4], bcc[4];
+      uint32_t bk[4], bab[4], bcc[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { best[k] = cv[o4][k]; bh[k] = ch[o4][k]; bl[k] = cl[o4][k]; bab[k] = cab[o4][k]; bcc[k] = 0; }
+      for (int k = 0; k < 4; ++k) { bk[k] = ck[o4][k]; bab[k] = (cab[o4] >> (8 * k)) & 0xffu; bcc[k] = 0; }
 #pragma unroll
       for (int cc = 1; cc < 3; ++cc)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float v = cv[o4 + cc][k];
-          const unsigned char ab = cab[o4 + cc][k];
-          if (v > best[k] || (v == best[k] && ab < bab[k])) {   // earlier (t,y) wins a tie; same (t,y): smaller x
-            best[k] = v; bh[k] = ch[o4 + cc][k]; bl[k] = cl[o4 + cc][k]; bab[k] = ab; bcc[k] = (unsigned char)cc;
+          const uint32_t v = ck[o4 + cc][k];
+          const uint32_t ab = (cab[o4 + cc] >> (8 * k)) & 0xffu;
+          if (v > bk[k] || (v == bk[k] && ab < bab[k])) {   // earlier (t,y) wins a tie; same (t,y): smaller x
+            bk[k] = v; bab[k] = ab; bcc[k] = (uint32_t)cc;
           }
         }
+      uint32_t oh[4], ol[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { oh[k] = f16_unsortable(bk[k] >> 16); ol[k] = f16_unsortable(bk[k] & 0xffffu); }
       const size_t o = ((((size_t)b * P.To + to) * P.Ho + yo) * P.Wo + xg * 4 + o4);
       const size_t oo = o * P.ldy + P.y_coff + c;
-      *reinterpret_cast<uint2*>(yh + oo) =
-          make_uint2((uint32_t)bh[0] | ((uint32_t)bh[1] << 16), (uint32_t)bh[2] | ((uint32_t)bh[3] << 16));
-      if (yl != nullptr)
-        *reinterpret_cast<uint2*>(yl + oo) =
-            make_uint2((uint32_t)bl[0] | ((uint32_t)bl[1] << 16), (uint32_t)bl[2] | ((uint32_t)bl[3] << 16));
+      *reinterpret_cast<uint2*>(yh + oo) = make_uint2(oh[0] | (oh[1] << 16), oh[2] | (oh[3] << 16));
+      if (yl != nullptr) *reinterpret_cast<uint2*>(yl + oo) = make_uint2(ol[0] | (ol[1] << 16), ol[2] | (ol[3] << 16));
       if (P.y2_hi != nullptr)
         st_pair4<true>(reinterpret_cast<uint16_t*>(P.y2_hi), reinterpret_cast<uint16_t*>(P.y2_lo), oo,
-                       make_float4(best[0], best[1], best[2], best[3]));
+                       make_float4(h2f((uint16_t)oh[0]) + h2f((uint16_t)ol[0]), h2f((uint16_t)oh[1]) + h2f((uint16_t)ol[1]),
+                                   h2f((uint16_t)oh[2]) + h2f((uint16_t)ol[2]), h2f((uint16_t)oh[3]) + h2f((uint16_t)ol[3])));
       if (P.idx)
         *reinterpret_cast<uchar4*>(P.idx + o * P.C + c) =
             make_uchar4((unsigned char)(bab[0] * 3 + bcc[0]), (unsigned char)(bab[1] * 3 + bcc[1]),

@@ -486,7 +486,8 @@ class Plan:
                     bnk = (((kreal + kt - 1) // kt) + 63) // 64 * 64
                     tiles = ((kreal + bnk - 1) // bnk) * ((it.cout + 127) // 128)
                     chunks = (a.M + 63) // 64
-                    splits = max(1, min(chunks, (2 * nsm + tiles - 1) // tiles))
+                    # tiles * splits CTAs, one per SM at a time: stay at or just under whole waves (<= 2 * #SMs)
+                    splits = max(1, min(chunks, (2 * nsm) // tiles))
                     wsrc = sa.plw.src(0, sa.spec.C, sa.dims[0], sa.dims[1], sa.dims[2])
                     wg = L.Wgrad(wsrc, geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin,
                                  L.dptr(st.view(it.name + ".weight", grad=True)), bnp, 1, 1, splits)
