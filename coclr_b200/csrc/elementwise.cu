@@ -296,6 +296,27 @@ __global__ void bias_relu_bwd_kernel(const float* h, const float* bias, float* d
 // Input and output are fp16 hi/lo planes (the arg-max element's pair is copied, so no re-rounding).
 // Compile-time window/stride for the four shapes S3D uses (0 = take the run-time value).
 // ------------------------------------------------------------------------------------------------
+// Comparisons stay in packed fp16: a value is the pair (hi, lo) with hi = round(value), so pairs order
+// lexicographically; __h*2_mask gives a 0xffff / 0 mask per 16-bit half, i.e. two channels per instruction and
+// no unpacking or conversion.
+COCLR_DEVINL __half2 u2h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+COCLR_DEVINL uint32_t pair_gt_mask(uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl) {
+  return __hgt2_mask(u2h2(ah), u2h2(bh)) | (__heq2_mask(u2h2(ah), u2h2(bh)) & __hgt2_mask(u2h2(al), u2h2(bl)));
+}
+COCLR_DEVINL uint32_t pair_eq_mask(uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl) {
+  return __heq2_mask(u2h2(ah), u2h2(bh)) & __heq2_mask(u2h2(al), u2h2(bl));
+}
+COCLR_DEVINL uint32_t msel(uint32_t a, uint32_t b, uint32_t m) { return (a & m) | (b & ~m); }
+// small non-negative integer n as an fp16 bit pattern replicated in both halves (exact for n <= 2048)
+COCLR_DEVINL uint32_t int_h2(int n) {
+  const uint32_t h = __half_as_ushort(__int2half_rn(n));
+  return h | (h << 16);
+}
+COCLR_DEVINL int h_lo_int(uint32_t u) { return __half2int_rn(__ushort_as_half((uint16_t)(u & 0xffffu))); }
+COCLR_DEVINL int h_hi_int(uint32_t u) { return __half2int_rn(__ushort_as_half((uint16_t)(u >> 16))); }
+
+static constexpr uint32_t kNegInf2 = 0xfc00fc00u;  // (-inf, -inf) in fp16
+
 template <int KT, int KH, int KW, int ST, int SH, int SW>
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const coclr_pool_t P) {
   const int kt = KT ? KT : P.g.kt, kh = KH ? KH : P.g.kh, kw = KW ? KW : P.g.kw;
@@ -314,9 +335,7 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const coclr_pool_t P) 
     const int to = (int)(r % P.To);
     const int b = (int)(r / P.To);
     const int c = cg * 4;
-    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    uint16_t bh[4] = {0xfc00, 0xfc00, 0xfc00, 0xfc00}, bl[4] = {0, 0, 0, 0};  // fp16 -inf
-    unsigned char bi[4] = {0, 0, 0, 0};
+    uint32_t bh[2] = {kNegInf2, kNegInf2}, bl[2] = {0u, 0u}, bt[2] = {0u, 0u};  // best hi / lo / tap (2 ch per word)
 #pragma unroll
     for (int a = 0; a < kt; ++a) {
       const int ti = to * st - P.g.pt + a;
@@ -329,34 +348,36 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const coclr_pool_t P) 
         for (int cc = 0; cc < kw; ++cc) {
           const int xi = xo * sw - P.g.pw + cc;
           if ((unsigned)xi >= (unsigned)P.Wi) continue;
-          const int tap = (a * kh + bb) * kw + cc;
+          const uint32_t tap2 = int_h2((a * kh + bb) * kw + cc);
           const size_t off = ((((size_t)b * P.Ti + ti) * P.Hi + yi) * P.Wi + xi) * P.ldx + P.x_coff + c;
           const uint2 h = *reinterpret_cast<const uint2*>(xh + off);
           uint2 l = make_uint2(0u, 0u);
           if (xl != nullptr) l = *reinterpret_cast<const uint2*>(xl + off);
-          const uint16_t hh[4] = {(uint16_t)(h.x & 0xffff), (uint16_t)(h.x >> 16), (uint16_t)(h.y & 0xffff),
-                                  (uint16_t)(h.y >> 16)};
-          const uint16_t ll[4] = {(uint16_t)(l.x & 0xffff), (uint16_t)(l.x >> 16), (uint16_t)(l.y & 0xffff),
-                                  (uint16_t)(l.y >> 16)};
+          const uint32_t hw[2] = {h.x, h.y}, lw[2] = {l.x, l.y};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float v = h2f(hh[j]) + h2f(ll[j]);
-            if (v > best[j]) { best[j] = v; bh[j] = hh[j]; bl[j] = ll[j]; bi[j] = (unsigned char)tap; }
+          for (int p = 0; p < 2; ++p) {
+            const uint32_t m = pair_gt_mask(hw[p], lw[p], bh[p], bl[p]);   // strictly greater: first max wins
+            bh[p] = msel(hw[p], bh[p], m);
+            bl[p] = msel(lw[p], bl[p], m);
+            bt[p] = msel(tap2, bt[p], m);
           }
         }
       }
     }
     const size_t o = ((((size_t)b * P.To + to) * P.Ho + yo) * P.Wo + xo);
     const size_t oo = o * P.ldy + P.y_coff + c;
-    *reinterpret_cast<uint2*>(yh + oo) =
-        make_uint2((uint32_t)bh[0] | ((uint32_t)bh[1] << 16), (uint32_t)bh[2] | ((uint32_t)bh[3] << 16));
-    if (yl != nullptr)
-      *reinterpret_cast<uint2*>(yl + oo) =
-          make_uint2((uint32_t)bl[0] | ((uint32_t)bl[1] << 16), (uint32_t)bl[2] | ((uint32_t)bl[3] << 16));
+    *reinterpret_cast<uint2*>(yh + oo) = make_uint2(bh[0], bh[1]);
+    if (yl != nullptr) *reinterpret_cast<uint2*>(yl + oo) = make_uint2(bl[0], bl[1]);
     if (P.y2_hi != nullptr)
       st_pair4<true>(reinterpret_cast<uint16_t*>(P.y2_hi), reinterpret_cast<uint16_t*>(P.y2_lo), oo,
-                     make_float4(best[0], best[1], best[2], best[3]));
-    if (P.idx) *reinterpret_cast<uchar4*>(P.idx + o * P.C + c) = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
+                     make_float4(h2f((uint16_t)(bh[0] & 0xffff)) + h2f((uint16_t)(bl[0] & 0xffff)),
+                                 h2f((uint16_t)(bh[0] >> 16)) + h2f((uint16_t)(bl[0] >> 16)),
+                                 h2f((uint16_t)(bh[1] & 0xffff)) + h2f((uint16_t)(bl[1] & 0xffff)),
+                                 h2f((uint16_t)(bh[1] >> 16)) + h2f((uint16_t)(bl[1] >> 16))));
+    if (P.idx)
+      *reinterpret_cast<uchar4*>(P.idx + o * P.C + c) =
+          make_uchar4((unsigned char)h_lo_int(bt[0]), (unsigned char)h_hi_int(bt[0]), (unsigned char)h_lo_int(bt[1]),
+                      (unsigned char)h_hi_int(bt[1]));
   }
 }
 
@@ -364,14 +385,7 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const coclr_pool_t P) 
 // produces 4 consecutive outputs along x for 4 channels and shares the loaded columns between them: first the
 // maximum over the 9 (t,y) taps of each of the 6 input columns, then 3 columns per output.  Ties resolve to the
 // first tap in (t,y,x) scan order like nn.MaxPool3d.
-// order-preserving map of an fp16 bit pattern to an unsigned integer (and back): value order == integer order
-COCLR_DEVINL uint32_t f16_sortable(uint32_t h) { return (h & 0x8000u) ? (~h & 0xffffu) : (h | 0x8000u); }
-COCLR_DEVINL uint32_t f16_unsortable(uint32_t k) { return (k & 0x8000u) ? (k & 0x7fffu) : (~k & 0xffffu); }
-// (hi, lo) pair -> one 32-bit key whose integer order is the order of hi + lo (hi is the rounded value, so
-// pairs compare lexicographically)
-COCLR_DEVINL uint32_t pair_key(uint32_t hh, uint32_t ll) { return (f16_sortable(hh) << 16) | f16_sortable(ll); }
-
-__global__ void __launch_bounds__(256, 3) maxpool333_fwd_kernel(const coclr_pool_t P) {
+__global__ void __launch_bounds__(256) maxpool333_fwd_kernel(const coclr_pool_t P) {
   const int C4 = P.C >> 2;
   const int XG = P.Wo >> 2;  // Wo % 4 == 0 checked by the launcher
   const long total = (long)P.B * P.To * P.Ho * XG * C4;
@@ -388,14 +402,11 @@ __global__ void __launch_bounds__(256, 3) maxpool333_fwd_kernel(const coclr_pool
     const int b = (int)(r / P.To);
     const int c = cg * 4;
     const int x0 = xg * 4 - 1;  // first input column
-    uint32_t ck[6][4];          // best key of each column over the 9 (t,y) taps (0 = below every real key)
-    uint32_t cab[6];            // 4 x 8-bit (t,y) tap index of that best, one byte per channel
+    uint32_t ch[6][2], cl[6][2], cab[6][2];  // per column: best hi / lo / (t,y) tap, 2 channels per word
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      cab[j] = 0;
+    for (int j = 0; j < 6; ++j)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) ck[j][k] = 0;
-    }
+      for (int p = 0; p < 2; ++p) { ch[j][p] = kNegInf2; cl[j][p] = 0u; cab[j][p] = 0u; }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const int ti = to - 1 + a;
@@ -404,7 +415,7 @@ __global__ void __launch_bounds__(256, 3) maxpool333_fwd_kernel(const coclr_pool
       for (int bb = 0; bb < 3; ++bb) {
         const int yi = yo - 1 + bb;
         if ((unsigned)yi >= (unsigned)P.Hi) continue;
-        const uint32_t ab = (uint32_t)(a * 3 + bb);
+        const uint32_t ab2 = int_h2(a * 3 + bb);
         const size_t rowoff = (((size_t)b * P.Ti + ti) * P.Hi + yi) * P.Wi;
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
@@ -414,47 +425,53 @@ __global__ void __launch_bounds__(256, 3) maxpool333_fwd_kernel(const coclr_pool
           const uint2 h = *reinterpret_cast<const uint2*>(xh + off);
           uint2 l = make_uint2(0u, 0u);
           if (xl != nullptr) l = *reinterpret_cast<const uint2*>(xl + off);
-          const uint32_t key[4] = {pair_key(h.x & 0xffffu, l.x & 0xffffu), pair_key(h.x >> 16, l.x >> 16),
-                                   pair_key(h.y & 0xffffu, l.y & 0xffffu), pair_key(h.y >> 16, l.y >> 16)};
+          const uint32_t hw[2] = {h.x, h.y}, lw[2] = {l.x, l.y};
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (key[k] > ck[j][k]) {
-              ck[j][k] = key[k];
-              cab[j] = (cab[j] & ~(0xffu << (8 * k))) | (ab << (8 * k));
-            }
+          for (int p = 0; p < 2; ++p) {
+            const uint32_t m = pair_gt_mask(hw[p], lw[p], ch[j][p], cl[j][p]);
+            ch[j][p] = msel(hw[p], ch[j][p], m);
+            cl[j][p] = msel(lw[p], cl[j][p], m);
+            cab[j][p] = msel(ab2, cab[j][p], m);
+          }
         }
       }
     }
 #pragma unroll
     for (int o4 = 0; o4 < 4; ++o4) {
-      uint32_t bk[4], bab[4], bcc[4];
+      uint32_t bh[2], bl[2], bab[2], bcc[2];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { bk[k] = ck[o4][k]; bab[k] = (cab[o4] >> (8 * k)) & 0xffu; bcc[k] = 0; }
+      for (int p = 0; p < 2; ++p) { bh[p] = ch[o4][p]; bl[p] = cl[o4][p]; bab[p] = cab[o4][p]; bcc[p] = 0u; }
 #pragma unroll
-      for (int cc = 1; cc < 3; ++cc)
+      for (int cc = 1; cc < 3; ++cc) {
+        const uint32_t cc2 = int_h2(cc);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t v = ck[o4 + cc][k];
-          const uint32_t ab = (cab[o4 + cc] >> (8 * k)) & 0xffu;
-          if (v > bk[k] || (v == bk[k] && ab < bab[k])) {   // earlier (t,y) wins a tie; same (t,y): smaller x
-            bk[k] = v; bab[k] = ab; bcc[k] = (uint32_t)cc;
-          }
+        for (int p = 0; p < 2; ++p) {
+          const uint32_t vh = ch[o4 + cc][p], vl = cl[o4 + cc][p], ab = cab[o4 + cc][p];
+          // greater, or equal with an earlier (t,y) tap (same (t,y): the smaller x stays)
+          const uint32_t m = pair_gt_mask(vh, vl, bh[p], bl[p]) |
+                             (pair_eq_mask(vh, vl, bh[p], bl[p]) & __hlt2_mask(u2h2(ab), u2h2(bab[p])));
+          bh[p] = msel(vh, bh[p], m);
+          bl[p] = msel(vl, bl[p], m);
+          bab[p] = msel(ab, bab[p], m);
+          bcc[p] = msel(cc2, bcc[p], m);
         }
-      uint32_t oh[4], ol[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { oh[k] = f16_unsortable(bk[k] >> 16); ol[k] = f16_unsortable(bk[k] & 0xffffu); }
+      }
       const size_t o = ((((size_t)b * P.To + to) * P.Ho + yo) * P.Wo + xg * 4 + o4);
       const size_t oo = o * P.ldy + P.y_coff + c;
-      *reinterpret_cast<uint2*>(yh + oo) = make_uint2(oh[0] | (oh[1] << 16), oh[2] | (oh[3] << 16));
-      if (yl != nullptr) *reinterpret_cast<uint2*>(yl + oo) = make_uint2(ol[0] | (ol[1] << 16), ol[2] | (ol[3] << 16));
+      *reinterpret_cast<uint2*>(yh + oo) = make_uint2(bh[0], bh[1]);
+      if (yl != nullptr) *reinterpret_cast<uint2*>(yl + oo) = make_uint2(bl[0], bl[1]);
       if (P.y2_hi != nullptr)
         st_pair4<true>(reinterpret_cast<uint16_t*>(P.y2_hi), reinterpret_cast<uint16_t*>(P.y2_lo), oo,
-                       make_float4(h2f((uint16_t)oh[0]) + h2f((uint16_t)ol[0]), h2f((uint16_t)oh[1]) + h2f((uint16_t)ol[1]),
-                                   h2f((uint16_t)oh[2]) + h2f((uint16_t)ol[2]), h2f((uint16_t)oh[3]) + h2f((uint16_t)ol[3])));
+                       make_float4(h2f((uint16_t)(bh[0] & 0xffff)) + h2f((uint16_t)(bl[0] & 0xffff)),
+                                   h2f((uint16_t)(bh[0] >> 16)) + h2f((uint16_t)(bl[0] >> 16)),
+                                   h2f((uint16_t)(bh[1] & 0xffff)) + h2f((uint16_t)(bl[1] & 0xffff)),
+                                   h2f((uint16_t)(bh[1] >> 16)) + h2f((uint16_t)(bl[1] >> 16))));
       if (P.idx)
         *reinterpret_cast<uchar4*>(P.idx + o * P.C + c) =
-            make_uchar4((unsigned char)(bab[0] * 3 + bcc[0]), (unsigned char)(bab[1] * 3 + bcc[1]),
-                        (unsigned char)(bab[2] * 3 + bcc[2]), (unsigned char)(bab[3] * 3 + bcc[3]));
+            make_uchar4((unsigned char)(h_lo_int(bab[0]) * 3 + h_lo_int(bcc[0])),
+                        (unsigned char)(h_hi_int(bab[0]) * 3 + h_hi_int(bcc[0])),
+                        (unsigned char)(h_lo_int(bab[1]) * 3 + h_lo_int(bcc[1])),
+                        (unsigned char)(h_hi_int(bab[1]) * 3 + h_hi_int(bcc[1])));
     }
   }
 }
