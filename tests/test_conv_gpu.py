@@ -211,9 +211,10 @@ POOLS = [((1, 3, 3), (1, 2, 2), (0, 1, 1)), ((3, 3, 3), (1, 1, 1), (1, 1, 1)), (
          ((2, 2, 2), (2, 2, 2), (0, 0, 0)), ((1, 2, 3), (1, 1, 2), (0, 1, 1))]
 
 
+@pytest.mark.parametrize("acc", [1, 0], ids=["accumulate", "overwrite"])
 @pytest.mark.parametrize("dims", [(6, 9, 10), (4, 8, 12)], ids=["ragged", "x4"])
 @pytest.mark.parametrize("k,s,p", POOLS, ids=["133s2", "333s1", "333s2", "222s2", "generic"])
-def test_maxpool_fwd_bwd(k, s, p, dims, diag):
+def test_maxpool_fwd_bwd(k, s, p, dims, acc, diag):
     import ctypes as C
     from coclr_b200 import ops, lib as L
     g = torch.Generator(device="cuda").manual_seed(13)
@@ -221,7 +222,7 @@ def test_maxpool_fwd_bwd(k, s, p, dims, diag):
     T, H, W = dims
     x = torch.randn(B, Cc, T, H, W, device="cuda", generator=g)
     x = torch.relu(x)                     # post-ReLU inputs as in the network: many exact ties at 0
-    pl, Cp, coff = _planes_of(ops, x, 0)
+    pl, Cp, coff = _planes_of(ops, x, 0) if acc else _planes_of(ops, x, 0, ld_extra=0, coff=0)
     xv = pl.value()[..., coff:coff + Cc].permute(0, 4, 1, 2, 3).double().requires_grad_(True)   # exact plane values
     ref = F.max_pool3d(xv, k, s, p)
     geom = ops.Geometry(k, s, p)
@@ -233,7 +234,7 @@ def test_maxpool_fwd_bwd(k, s, p, dims, diag):
     tw = ops.Planes((B, To, Ho, Wo, Cp), 1, "cuda")
     pp = L.Pool(L.dptr(pl.hi), L.dptr(pl.lo), pl.ld, coff, L.dptr(out.hi), L.dptr(out.lo), Cp, 0,
                 L.dptr(tw.hi), L.dptr(tw.lo), L.dptr(idx),
-                B, Cp, T, H, W, To, Ho, Wo, geom.c(0), L.dptr(dyt), L.dptr(dx), 1)
+                B, Cp, T, H, W, To, Ho, Wo, geom.c(0), L.dptr(dyt), L.dptr(dx), acc)
     L.check(L.load().coclr_maxpool_fwd(C.byref(pp), L.stream_ptr()), "coclr_maxpool_fwd")
     L.check(L.load().coclr_maxpool_bwd(C.byref(pp), L.stream_ptr()), "coclr_maxpool_bwd")
     torch.cuda.synchronize()
@@ -241,7 +242,7 @@ def test_maxpool_fwd_bwd(k, s, p, dims, diag):
     assert torch.equal(got.double(), ref.detach())
     assert _rel(tw.value()[..., :Cc].permute(0, 4, 1, 2, 3), ref.detach()) < 2e-5
     (gref,) = torch.autograd.grad(ref, xv, dyt[..., :Cc].permute(0, 4, 1, 2, 3).double())
-    gdx = (dx[..., coff:coff + Cc] - 0.5).permute(0, 4, 1, 2, 3)
+    gdx = (dx[..., coff:coff + Cc] - (0.5 if acc else 0.0)).permute(0, 4, 1, 2, 3)
     e = _rel(gdx, gref)
     diag["pool/%s" % (str(k) + str(s))] = e
     assert e < 1e-6
