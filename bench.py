@@ -152,7 +152,9 @@ def conv_flops(cv):
         pix = cv.B * cv.src.T * cv.src.H * cv.src.W
         return 2.0 * pix * cv.N * cv.g.kt * cv.g.kh * cv.g.kw * cv.src.C
     pix = cv.B * cv.Td * cv.Hd * cv.Wd
-    cin = 3 if cv.src.C == 8 else cv.src.C   # the RGB stem input is stored with 5 zero channels (C padded to 8)
+    if cv.src.C == 16 and cv.g.kh == 4 and cv.g.kw == 4:   # space-to-depth stem: the 7x7x3 conv it implements
+        return 2.0 * pix * cv.N * 147
+    cin = 3 if cv.src.C == 8 else cv.src.C   # RGB input padded to 8 channels when the s2d stem is off
     return 2.0 * pix * cv.N * cv.g.kt * cv.g.kh * cv.g.kw * cin
 
 

@@ -627,6 +627,40 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* x, long ba
   }
 }
 
+// Space-to-depth variant for the stride-2 7x7 stem (backbone/s3dg.py:145): out[b, t, Y, X, (dy*2+dx)*Cin + c] =
+// x[b, c, t, 2Y+dy, 2X+dx], 16 channels per pixel (4*Cin = 12 real + zeros).  The stem then is a stride-1
+// 4x4 convolution over 16-channel pixels: 32-byte gather granules and 16 instead of 49 taps.
+__global__ void __launch_bounds__(256) pack_input_s2d_kernel(const float* x, long batch_stride, long chan_stride,
+                                                             int Cin, uint16_t* out_hi, uint16_t* out_lo,
+                                                             uint16_t* out2_hi, uint16_t* out2_lo, int B, int T, int H,
+                                                             int W, const long* __restrict__ batch_index) {
+  const int H2 = H >> 1, W2 = W >> 1;
+  const long total = (long)B * T * H2 * W2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W2);
+    long r = i / W2;
+    const int Y = (int)(r % H2); r /= H2;
+    const int t = (int)(r % T);
+    const long b = r / T;
+    const long sb = batch_index ? batch_index[b] : b;
+    const float* s = x + sb * batch_stride + ((long)t * H + 2 * Y) * W + 2 * X;
+    float vv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) vv[j] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx)
+        for (int c = 0; c < Cin; ++c) vv[(dy * 2 + dx) * Cin + c] = s[(long)c * chan_stride + dy * W + dx];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v4 = make_float4(vv[4 * q], vv[4 * q + 1], vv[4 * q + 2], vv[4 * q + 3]);
+      st_pair4<false>(out_hi, out_lo, (size_t)i * 16 + 4 * q, v4);
+      if (out2_hi != nullptr) st_pair4<true>(out2_hi, out2_lo, (size_t)i * 16 + 4 * q, v4);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // F.normalize(z + bias, dim=1) (model/pretrain.py:154,167) and backward; one warp per row
 // ------------------------------------------------------------------------------------------------
@@ -852,6 +886,17 @@ extern "C" int coclr_pack_input(const float* x, long batch_stride, long chan_str
   pack_input_kernel<<<grid_for((long)B * thw, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
       x, batch_stride, chan_stride, Cin, reinterpret_cast<uint16_t*>(out_hi), reinterpret_cast<uint16_t*>(out_lo),
       reinterpret_cast<uint16_t*>(out2_hi), reinterpret_cast<uint16_t*>(out2_lo), B, thw, batch_index);
+  return LAUNCH_OK();
+}
+
+extern "C" int coclr_pack_input_s2d(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi,
+                                    void* out_lo, void* out2_hi, void* out2_lo, int B, int T, int H, int W,
+                                    const long* batch_index, coclr_stream_t stream) {
+  if (!x || !out_hi || Cin < 1 || Cin > 4 || (H & 1) || (W & 1)) return COCLR_E_ARG;
+  const long total = (long)B * T * (H / 2) * (W / 2);
+  pack_input_s2d_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      x, batch_stride, chan_stride, Cin, reinterpret_cast<uint16_t*>(out_hi), reinterpret_cast<uint16_t*>(out_lo),
+      reinterpret_cast<uint16_t*>(out2_hi), reinterpret_cast<uint16_t*>(out2_lo), B, T, H, W, batch_index);
   return LAUNCH_OK();
 }
 

@@ -50,6 +50,9 @@ class ConvSpec:
         self.name, self.src, self.dst, self.dst_coff = name, src, dst, dst_coff
         self.cin, self.cout, self.k, self.s, self.p = cin, cout, k, s, p
         self.bias, self.need_dgrad = bias, need_dgrad
+        # what the kernels see; differs from the parameter's own shape only for the space-to-depth stem
+        self.s2d = False
+        self.cin_eff, self.k_eff, self.s_eff, self.p_eff = cin, k, s, p
 
 
 class PoolSpec:
@@ -82,14 +85,23 @@ class _LaneList(list):
 class Graph:
     """Shape-independent description of the encoder: tensors, convs, pools in forward order."""
 
-    def __init__(self, stages, first_channel=3, head_dim=None, feature_size=S3D_FEATURE_SIZE, bb_prefix=""):
+    def __init__(self, stages, first_channel=3, head_dim=None, feature_size=S3D_FEATURE_SIZE, bb_prefix="",
+                 stem_s2d=True):
         self.tensors, self.items = [], _LaneList(self)   # items: ("conv", ConvSpec) | ("pool", PoolSpec) | ("bn", TensorSpec)
         self.item_lane, self.item_flag = [], []   # per item: stream lane (Inception branches run concurrently) and FORK/JOIN
         self.cur_lane, self.next_flag = 0, 0
         self.first_channel = first_channel
         self.head_dim, self.feature_size = head_dim, feature_size
         pre = bb_prefix
-        x = self._tensor("input", _round8(first_channel), lambda d: d, pending=False)
+        st0 = stages[0]
+        # stride-2 7x7 RGB stem as a stride-1 4x4 conv over a space-to-depth input (16 channels / pixel): 16 taps of
+        # 32-byte granules instead of 49 taps of 16-byte granules
+        self.stem_s2d = bool(stem_s2d and st0[0] == "st" and st0[4] == 7 and st0[5] == 2 and st0[7] == 3
+                             and 4 * first_channel <= 16)
+        if self.stem_s2d:
+            x = self._tensor("input", 16, lambda d: (d[0], d[1] // 2, d[2] // 2), pending=False)
+        else:
+            x = self._tensor("input", _round8(first_channel), lambda d: d, pending=False)
         self.input = x
         first_conv = True
         for stg in stages:
@@ -139,8 +151,11 @@ class Graph:
     def _st(self, name, x, dst, dst_coff, cin, cout, k, ss, ts, pad, need_dgrad=True):
         k1, s1, p1 = (1, k, k), (1, ss, ss), (0, pad, pad)
         k2, s2, p2 = (k, 1, 1), (ts, 1, 1), (pad, 0, 0)
-        mid = self._tensor(name + ".mid", cout, self._after(x, k1, s1, p1))
-        self._conv(name + ".conv1", x, mid, 0, cin, cout, k1, s1, p1, need_dgrad=need_dgrad)
+        s2d = (not need_dgrad) and self.stem_s2d and x is self.input
+        mid = self._tensor(name + ".mid", cout, self._same(x) if s2d else self._after(x, k1, s1, p1))
+        cv = self._conv(name + ".conv1", x, mid, 0, cin, cout, k1, s1, p1, need_dgrad=need_dgrad)
+        if s2d:
+            cv.s2d, cv.cin_eff, cv.k_eff, cv.s_eff, cv.p_eff = True, 4 * cin, (1, 4, 4), (1, 1, 1), (0, 2, 2)
         mid.bn_members.append((name + ".bn1", 0, cout))
         self.items.append(("bn", mid))
         own = dst is None
@@ -355,7 +370,7 @@ class Plan:
             n_before = len(self.fwd)
             if kind == "conv":
                 sa, da = acts[it.src.index], acts[it.dst.index]
-                geom = ops.Geometry(it.k, it.s, it.p)
+                geom = ops.Geometry(it.k_eff, it.s_eff, it.p_eff)
                 pw = eng.packed_fwd[it.name]
                 cv = ops.make_conv(src_of(sa), fbf, geom.c(0), B, da.dims, pw, da.data, it.dst_coff,
                                    stats_sum=da.ssum[it.dst_coff:] if training else None,
@@ -479,7 +494,7 @@ class Plan:
                 bw.append((lib.coclr_bn_bwd, (C.byref(bb), nsm)))
                 for it in convs_into[t.index]:
                     sa = acts[it.src.index]
-                    geom = ops.Geometry(it.k, it.s, it.p)
+                    geom = ops.Geometry(it.k_eff, it.s_eff, it.p_eff)
                     dy = a.dy.src(it.dst_coff, _round8(it.cout), a.dims[0], a.dims[1], a.dims[2])
                     kreal = geom.taps * it.src.C
                     kt = (kreal + 255) // 256
@@ -489,10 +504,18 @@ class Plan:
                     # tiles * splits CTAs, one per SM at a time: stay at or just under whole waves (<= 2 * #SMs)
                     splits = max(1, min(chunks, (2 * nsm) // tiles))
                     wsrc = sa.plw.src(0, sa.spec.C, sa.dims[0], sa.dims[1], sa.dims[2])
-                    wg = L.Wgrad(wsrc, geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin,
-                                 L.dptr(st.view(it.name + ".weight", grad=True)), bnp, 1, 1, splits)
-                    self.keep += [wg, dy]
-                    bw.append((lib.coclr_conv_wgrad, (C.byref(wg),)))
+                    if it.s2d:
+                        # the weight gradient is produced in the space-to-depth layout, then scattered back
+                        dw_eff = eng.s2d[it.name]["dw_eff"]
+                        wg = L.Wgrad(wsrc, geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin_eff,
+                                     L.dptr(dw_eff), bnp, 1, 1, splits)
+                        self.keep += [wg, dy]
+                        bw.append((eng._s2d_wgrad_op(it.name, wg), ()))
+                    else:
+                        wg = L.Wgrad(wsrc, geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin,
+                                     L.dptr(st.view(it.name + ".weight", grad=True)), bnp, 1, 1, splits)
+                        self.keep += [wg, dy]
+                        bw.append((lib.coclr_conv_wgrad, (C.byref(wg),)))
                     if it.need_dgrad:
                         dg = ops.make_conv(dy, 1, geom.c(1), B, sa.dims, eng.packed_bwd[it.name], sa.grad, 0,
                                            accumulate=sa.grad_written, npass=bnp)
@@ -527,9 +550,11 @@ class EncoderEngine:
         for kind, it in graph.items:
             if kind != "conv":
                 continue
-            taps = it.k[0] * it.k[1] * it.k[2]
+            taps = it.k_eff[0] * it.k_eff[1] * it.k_eff[2]
             w = store.view(it.name + ".weight")
-            pf = ops.PackedWeights(it.cout, it.cin, taps, it.src.C, 0, fbf, dev)
+            if it.s2d:
+                w = self._make_s2d(it, w, dev)
+            pf = ops.PackedWeights(it.cout, it.cin_eff, taps, it.src.C, 0, fbf, dev)
             self.packed_fwd[it.name] = pf
             self._packs.append((pf, w, False))
             if it.need_dgrad:
@@ -545,8 +570,52 @@ class EncoderEngine:
                 self.packed_fwd[nm], self.packed_bwd[nm] = pf, pb
                 self._packs += [(pf, w, False), (pb, w, True)]
 
+    def _make_s2d(self, it, w, dev):
+        """Index map of the space-to-depth stem: W'[o, (dy*2+dx)*Cin + c, 0, ty, tx] = W[o, c, 0, 2ty+dy-1, 2tx+dx-1]
+        (zero when an index is -1).  Returns the persistent W' tensor that is re-derived before every packing."""
+        cout, cin = it.cout, it.cin
+        idx = torch.zeros(cout, 4 * cin, 1, 4, 4, dtype=torch.long)
+        msk = torch.zeros(cout, 4 * cin, 1, 4, 4, dtype=torch.float32)
+        o = torch.arange(cout).view(-1, 1)
+        for dy in range(2):
+            for dx in range(2):
+                for ty in range(4):
+                    for tx in range(4):
+                        ky, kx = 2 * ty + dy - 1, 2 * tx + dx - 1
+                        if ky < 0 or kx < 0:
+                            continue
+                        for c in range(cin):
+                            idx[:, (dy * 2 + dx) * cin + c, 0, ty, tx] = ((o[:, 0] * cin + c) * 7 + ky) * 7 + kx
+                            msk[:, (dy * 2 + dx) * cin + c, 0, ty, tx] = 1.0
+        d = {"idx": idx.to(dev).view(-1), "mask": msk.to(dev).view(-1), "w": w,
+             "w_eff": torch.zeros(cout, 4 * cin, 1, 4, 4, device=dev),
+             "dw_eff": torch.zeros(cout, 4 * cin, 1, 4, 4, device=dev),
+             "dw": self.store.view(it.name + ".weight", grad=True)}
+        if not hasattr(self, "s2d"):
+            self.s2d = {}
+        self.s2d[it.name] = d
+        return d["w_eff"]
+
+    def _refresh_s2d(self):
+        for d in getattr(self, "s2d", {}).values():
+            torch.mul(d["w"].reshape(-1)[d["idx"]], d["mask"], out=d["w_eff"].view(-1))
+
+    def _s2d_wgrad_op(self, name, wg):
+        d = self.s2d[name]
+        lib = L.load()
+
+        def op(stream):
+            d["dw_eff"].zero_()
+            rc = lib.coclr_conv_wgrad(C.byref(wg), stream)
+            # W' -> W is one-to-one on the valid entries (masked entries point at index 0 with a zero factor)
+            d["dw"].view(-1).index_add_(0, d["idx"], d["dw_eff"].view(-1) * d["mask"])
+            return rc
+        op.__name__ = "coclr_conv_wgrad_s2d"
+        return op
+
     def pack_weights(self, backward=True):
         """Re-derive the 16-bit hi/lo tile images from the current fp32 weights."""
+        self._refresh_s2d()
         for pw, w, is_bwd in self._packs:
             if is_bwd and not backward:
                 continue
@@ -641,10 +710,17 @@ class EncoderEngine:
         lib = L.load()
         tw = p.input.plw if (p.input.plw is not None and p.input.plw is not p.input.pl) else None
         # the clip pointer / shuffle index change from call to call, so packing stays outside the captured graph
-        L.check(lib.coclr_pack_input(L.dptr(x), x.stride(0), x.stride(1), Cin, L.dptr(p.input.pl.hi),
-                                     L.dptr(p.input.pl.lo), L.dptr(tw.hi) if tw else None,
-                                     L.dptr(tw.lo) if tw else None, B, T * H * W, L.dptr(batch_index), L.stream_ptr()),
-                "coclr_pack_input")
+        if self.graph.stem_s2d:
+            assert H % 2 == 0 and W % 2 == 0, "the space-to-depth stem needs even H, W"
+            L.check(lib.coclr_pack_input_s2d(L.dptr(x), x.stride(0), x.stride(1), Cin, L.dptr(p.input.pl.hi),
+                                             L.dptr(p.input.pl.lo), L.dptr(tw.hi) if tw else None,
+                                             L.dptr(tw.lo) if tw else None, B, T, H, W, L.dptr(batch_index),
+                                             L.stream_ptr()), "coclr_pack_input_s2d")
+        else:
+            L.check(lib.coclr_pack_input(L.dptr(x), x.stride(0), x.stride(1), Cin, L.dptr(p.input.pl.hi),
+                                         L.dptr(p.input.pl.lo), L.dptr(tw.hi) if tw else None,
+                                         L.dptr(tw.lo) if tw else None, B, T * H * W, L.dptr(batch_index),
+                                         L.stream_ptr()), "coclr_pack_input")
 
         def body():
             if repack:

@@ -210,6 +210,12 @@ int coclr_pack_input(const float* x, long batch_stride, long chan_stride, int Ci
                      void* out2_hi, void* out2_lo /* optional bf16 twin */, int B, long thw, const long* batch_index,
                      coclr_stream_t stream);
 
+/* space-to-depth variant for the stride-2 7x7 RGB stem (backbone/s3dg.py:145): planes [B, T, H/2, W/2, 16] with
+ * channel (dy*2+dx)*Cin + c = x[b, c, t, 2Y+dy, 2X+dx] (4*Cin real channels, rest zero); H, W even */
+int coclr_pack_input_s2d(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi, void* out_lo,
+                         void* out2_hi, void* out2_lo, int B, int T, int H, int W, const long* batch_index,
+                         coclr_stream_t stream);
+
 /* ---- F.normalize(z + bias, dim=1) (model/pretrain.py:154,167) ------------------------------------- */
 int coclr_l2norm_fwd(const float* z, const float* bias, float* q, float* inv_norm, int B, int D, coclr_stream_t stream);
 int coclr_l2norm_bwd(const float* q, const float* dq, const float* inv_norm, float* dz, float* dbias, int B, int D,
