@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 REF = "/root/reference"
 
 
-def make_inputs(B=4, T=8, HW=128, seed=1234):
+def make_inputs(B=4, T=8, HW=128, seed=1234):  # noqa
     g = torch.Generator().manual_seed(seed)
     return torch.randn(B, 2, 3, T, HW, HW, generator=g)
 
