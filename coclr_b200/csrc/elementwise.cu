@@ -192,9 +192,7 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_reduce_kernel(const coclr_
     const long rows_per = ((long)P.M + gridDim.x - 1) / gridDim.x;
     const long r_begin = (long)blockIdx.x * rows_per;
     const long r_end = min((long)P.M, r_begin + rows_per);
-    for (long r = r_begin + rs; r < r_end; r += R) {
-      const float4 y = ld4(P.y + r * P.ld + P.coff + c);
-      const float4 da = ld4(P.dA + r * P.ld + P.coff + c);
+    auto body = [&](const float4& y, const float4& da) {
       float4 dz;
       dz.x = (!P.relu || fmaf(y.x, sc.x, sh.x) > 0.f) ? da.x : 0.f;
       dz.y = (!P.relu || fmaf(y.y, sc.y, sh.y) > 0.f) ? da.y : 0.f;
@@ -205,7 +203,19 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_reduce_kernel(const coclr_
       acc[5] += dz.y * ((y.y - mu.y) * rs4.y);
       acc[6] += dz.z * ((y.z - mu.z) * rs4.z);
       acc[7] += dz.w * ((y.w - mu.w) * rs4.w);
+    };
+    long r = r_begin + rs;
+    for (; r + 3 * R < r_end; r += 4 * R) {   // 8 independent 16-byte loads in flight per thread
+      float4 y[4], da[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        y[u] = ld4(P.y + (r + u * R) * P.ld + P.coff + c);
+        da[u] = ld4(P.dA + (r + u * R) * P.ld + P.coff + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) body(y[u], da[u]);
     }
+    for (; r < r_end; r += R) body(ld4(P.y + r * P.ld + P.coff + c), ld4(P.dA + r * P.ld + P.coff + c));
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) red[j][t] = acc[j];
@@ -251,10 +261,7 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(const coclr_b
   const long rows_per = ((long)P.M + gridDim.x - 1) / gridDim.x;
   const long r_begin = (long)blockIdx.x * rows_per;
   const long r_end = min((long)P.M, r_begin + rows_per);
-  for (long r = r_begin + rs; r < r_end; r += R) {
-    const size_t off = (size_t)(r * P.ld + P.coff + c);
-    const float4 y = ld4(P.y + off);
-    const float4 da = ld4(P.dA + off);
+  auto body = [&](size_t off, const float4& y, const float4& da) {
     float4 o;
     {
       const float dz = (!P.relu || fmaf(y.x, sc.x, sh.x) > 0.f) ? da.x : 0.f;
@@ -273,6 +280,23 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(const coclr_b
       o.w = sc.w * (dz - m1[3] - ((y.w - mu.w) * rs4.w) * m2[3]);
     }
     st_pair4<true>(hi, lo, off, o);
+  };
+  long r = r_begin + rs;
+  for (; r + 3 * R < r_end; r += 4 * R) {
+    float4 y[4], da[4];
+    size_t off[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      off[u] = (size_t)((r + u * R) * P.ld + P.coff + c);
+      y[u] = ld4(P.y + off[u]);
+      da[u] = ld4(P.dA + off[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) body(off[u], y[u], da[u]);
+  }
+  for (; r < r_end; r += R) {
+    const size_t off = (size_t)(r * P.ld + P.coff + c);
+    body(off, ld4(P.y + off), ld4(P.dA + off));
   }
 }
 
