@@ -146,7 +146,7 @@ struct ConvSmemLayout {
   uint32_t stage_bytes;  // all copies of A and B of one stage
   uint32_t stages;
   uint32_t off_stage;    // transpose staging for the epilogue
-  uint32_t off_stats;    // double [2][n_tiles*BN]
+  uint32_t off_stats;    // float [epilogue warps][2][n_tiles*BN + 4]: per-warp BN-statistic partial sums
   uint32_t off_bars;
   uint32_t total;
 };
@@ -157,14 +157,15 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(int BN, int n_tiles, 
   L.a_bytes = kTileM * 128u;
   L.b_bytes = (uint32_t)BN * 128u;
   L.stage_bytes = copies * (L.a_bytes + L.b_bytes);
-  const uint32_t fixed = kEpiWarps * 32u * kStagePitch * 4u + (want_stats ? 2u * n_tiles * BN * 8u : 0u) + 256u;
+  const uint32_t stat_bytes = want_stats ? kEpiWarps * 2u * (uint32_t)(n_tiles * BN + 4) * 4u : 0u;
+  const uint32_t fixed = kEpiWarps * 32u * kStagePitch * 4u + stat_bytes + 256u;
   const uint32_t budget = 227u * 1024u - 1024u /*alignment slack*/ - fixed;
   uint32_t st = budget / L.stage_bytes;
   if (st > (uint32_t)kMaxStages) st = kMaxStages;
   L.stages = st;
   L.off_stage = L.stages * L.stage_bytes;
   L.off_stats = L.off_stage + kEpiWarps * 32u * kStagePitch * 4u;
-  L.off_bars = L.off_stats + (want_stats ? 2u * n_tiles * BN * 8u : 0u);
+  L.off_bars = (L.off_stats + stat_bytes + 15u) & ~15u;
   L.total = L.off_bars + 256u + 1024u;
   return L;
 }
@@ -182,7 +183,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
   const uint32_t nstages = L.stages;
 
   float* stage_buf = reinterpret_cast<float*>(smem + L.off_stage);
-  double* sstats = reinterpret_cast<double*>(smem + L.off_stats);
+  float* wstats = reinterpret_cast<float*>(smem + L.off_stats);
+  const int stat_cols = P.n_tiles * P.BN + 4;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.off_bars);  // [kMaxStages]
   uint64_t* empty_bar = full_bar + kMaxStages;                           // [kMaxStages]
   uint64_t* tfull_bar = empty_bar + kMaxStages;                          // [2]
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
     mbar_fence_init();
   }
   if (P.stats_sum != nullptr) {
-    for (int i = threadIdx.x; i < 2 * P.n_tiles * P.BN; i += kThreads) sstats[i] = 0.0;
+    for (int i = threadIdx.x; i < kEpiWarps * 2 * stat_cols; i += kThreads) wstats[i] = 0.f;
   }
   if (warp == 13) {
     tmem_alloc<512>(tmem_holder);
@@ -310,6 +312,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
       tc_fence_after();
       const int row_base = m_tile * kTileM + warp * 32;
       const int rows_here = min(32, M - row_base);
+      // store mapping after the transpose: lane = (row group rg, column quad cq); one 16-byte store per lane covers
+      // 4 rows x 128 B per warp instruction
+      const int rg = lane >> 3, cq = lane & 7;
       for (int c0 = 0; c0 < P.BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 256u + (uint32_t)c0, v);
@@ -317,35 +322,56 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
 #pragma unroll
         for (int j = 0; j < 32; ++j) my_stage[lane * kStagePitch + j] = __uint_as_float(v[j]);
         __syncwarp();
-        const int col = n_tile * P.BN + c0 + lane;  // global output channel handled by this lane
-        const bool col_ok = col < P.N;
-        const float us = (P.wunscale != nullptr && col_ok) ? __ldg(P.wunscale + n_tile * P.BN + c0 + lane) : 1.f;
-        float s1 = 0.f, s2 = 0.f;
-        if (col_ok && rows_here > 0) {
-          float* d = P.dst + (size_t)row_base * P.dst_ld + P.dst_coff + col;
-          if (P.accumulate) {
-            // read-modify-write: batch the loads (8 in flight per lane) instead of one dependent load per row
-            for (int r0 = 0; r0 < rows_here; r0 += 8) {
-              float old[8];
+        const int colq = n_tile * P.BN + c0 + cq * 4;  // first of this lane's 4 output channels
+        float us[4] = {1.f, 1.f, 1.f, 1.f};
+        if (P.wunscale != nullptr) {
+          const float4 u4 = __ldg(reinterpret_cast<const float4*>(P.wunscale + n_tile * P.BN + c0 + cq * 4));
+          us[0] = u4.x; us[1] = u4.y; us[2] = u4.z; us[3] = u4.w;
+        }
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool full_quad = colq + 3 < P.N;
+        if (colq < P.N) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) old[j] = (r0 + j < rows_here) ? d[(size_t)(r0 + j) * P.dst_ld] : 0.f;
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (r0 + j < rows_here)
-                  d[(size_t)(r0 + j) * P.dst_ld] = fmaf(my_stage[(r0 + j) * kStagePitch + lane], us, old[j]);
-            }
-          } else {
-#pragma unroll 8
-            for (int r = 0; r < rows_here; ++r, d += P.dst_ld) {
-              const float val = my_stage[r * kStagePitch + lane] * us;
-              *d = val;
-              s1 += val;
-              s2 = fmaf(val, val, s2);
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rg;
+            if (r < rows_here) {
+              const float* sp = my_stage + r * kStagePitch + cq * 4;
+              float4 val = make_float4(sp[0] * us[0], sp[1] * us[1], sp[2] * us[2], sp[3] * us[3]);
+              float* d = P.dst + (size_t)(row_base + r) * P.dst_ld + P.dst_coff + colq;
+              if (full_quad) {
+                if (P.accumulate) {
+                  const float4 old = *reinterpret_cast<const float4*>(d);
+                  val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+                }
+                *reinterpret_cast<float4*>(d) = val;
+              } else {
+                const float vv[4] = {val.x, val.y, val.z, val.w};
+                for (int k = 0; k < 4; ++k)
+                  if (colq + k < P.N) d[k] = P.accumulate ? d[k] + vv[k] : vv[k];
+              }
+              s1[0] += val.x; s1[1] += val.y; s1[2] += val.z; s1[3] += val.w;
+              s2[0] = fmaf(val.x, val.x, s2[0]); s2[1] = fmaf(val.y, val.y, s2[1]);
+              s2[2] = fmaf(val.z, val.z, s2[2]); s2[3] = fmaf(val.w, val.w, s2[3]);
             }
           }
-          if (P.stats_sum != nullptr) {
-            atomicAdd(&sstats[col], (double)s1);
-            atomicAdd(&sstats[P.n_tiles * P.BN + col], (double)s2);
+        }
+        if (P.stats_sum != nullptr) {
+          // column sums over the warp's 32 rows: combine the 4 row groups, then one owner lane per column quad
+          // accumulates into this warp's private fp32 table (no atomics; flushed in fp64 at the end)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 8);
+            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 16);
+            s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], 8);
+            s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], 16);
+          }
+          if (rg == 0 && colq < P.N) {
+            float* ws = wstats + (size_t)warp * 2 * stat_cols;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              ws[colq + k] += s1[k];
+              ws[stat_cols + colq + k] += s2[k];
+            }
           }
         }
         __syncwarp();
@@ -357,8 +383,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
     if (P.stats_sum != nullptr) {
       named_bar_sync(1, kEpiWarps * 32);
       for (int c = threadIdx.x; c < P.N; c += kEpiWarps * 32) {
-        atomicAdd(&P.stats_sum[c], sstats[c]);
-        atomicAdd(&P.stats_sq[c], sstats[P.n_tiles * P.BN + c]);
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int w = 0; w < kEpiWarps; ++w) {
+          a += (double)wstats[(size_t)w * 2 * stat_cols + c];
+          b += (double)wstats[(size_t)w * 2 * stat_cols + stat_cols + c];
+        }
+        atomicAdd(&P.stats_sum[c], a);
+        atomicAdd(&P.stats_sq[c], b);
       }
     }
   }
@@ -684,6 +716,7 @@ extern "C" int coclr_conv_igemm(const coclr_conv_t* p, int num_sms, coclr_stream
   if (!p || !p->wpk || !p->dst) return COCLR_E_ARG;
   if (!src_ok(p->src, p->npass > 1)) return COCLR_E_ARG;
   if (p->BN % 32 != 0 || p->BN > 256 || p->BN < 32 || p->n_tiles < 1) return COCLR_E_ARG;
+  if (p->dst_ld % 4 != 0 || p->dst_coff % 4 != 0 || ((uintptr_t)p->dst & 15)) return COCLR_E_ARG;  // 16-byte stores
   if (p->Kreal != p->g.kt * p->g.kh * p->g.kw * p->src.C) return COCLR_E_ARG;
   if ((p->g.st != 1 && p->g.st != 2) || (p->g.sh != 1 && p->g.sh != 2) || (p->g.sw != 1 && p->g.sw != 2))
     return COCLR_E_ARG;
