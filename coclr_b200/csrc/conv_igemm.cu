@@ -331,6 +331,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
         const bool full_quad = colq + 3 < P.N;
         if (colq < P.N) {
+          // read-modify-write destinations: issue all 8 loads of this chunk before the first store (the compiler
+          // must otherwise keep each load behind the previous store)
+          float4 old[8];
+          if (P.accumulate && full_quad) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + rg;
+              old[it] = (r < rows_here)
+                            ? *reinterpret_cast<const float4*>(P.dst + (size_t)(row_base + r) * P.dst_ld + P.dst_coff + colq)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + rg;
@@ -340,8 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
               float* d = P.dst + (size_t)(row_base + r) * P.dst_ld + P.dst_coff + colq;
               if (full_quad) {
                 if (P.accumulate) {
-                  const float4 old = *reinterpret_cast<const float4*>(d);
-                  val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+                  val.x += old[it].x; val.y += old[it].y; val.z += old[it].z; val.w += old[it].w;
                 }
                 *reinterpret_cast<float4*>(d) = val;
               } else {
