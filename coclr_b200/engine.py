@@ -502,7 +502,9 @@ class Plan:
                     tiles = ((kreal + bnk - 1) // bnk) * ((it.cout + 127) // 128)
                     chunks = (a.M + 63) // 64
                     # tiles * splits CTAs, one per SM at a time: stay at or just under whole waves (<= 2 * #SMs)
-                    splits = max(1, min(chunks, (2 * nsm) // tiles))
+                    # ... and every split should own >= 16 pixel chunks: each split ends with Cout x K fp32 atomics,
+                    # which dominate when the pixel range per CTA is short
+                    splits = max(1, min(chunks // 16 if chunks >= 16 else 1, (2 * nsm) // tiles))
                     wsrc = sa.plw.src(0, sa.spec.C, sa.dims[0], sa.dims[1], sa.dims[2])
                     if it.s2d:
                         # the weight gradient is produced in the space-to-depth layout, then scattered back
