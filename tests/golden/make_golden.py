@@ -1,4 +1,4 @@
-"""Generates tests/golden/infonce_cfg1.npz by running the UNMODIFIED reference (TengdaHan/CoCLR at
+"""Generates tests/golden/infonce_cfg1.npz (and, with the argument `r50`, infonce_r50.npz) by running the UNMODIFIED reference (TengdaHan/CoCLR at
 /root/reference, model/pretrain.py InfoNCE) on BASELINE.json config 1 (S3D, moco-k=128, bs=4,
 seq_len=8, 128x128, CPU) from the deterministic synthetic state of oracle.coclr_oracle.synth_state.
 
@@ -21,6 +21,25 @@ REF = "/root/reference"
 def make_inputs(B=4, T=8, HW=128, seed=1234):  # noqa
     g = torch.Generator().manual_seed(seed)
     return torch.randn(B, 2, 3, T, HW, HW, generator=g)
+
+
+def make_inputs_shifted(B=4, T=8, HW=64, seed=1234):  # noqa
+    """Noise clips plus a per-clip colour offset and a per-clip spatial ramp, so that clips stay distinguishable after
+    the global average pool (pure noise gives q == k for every pair and a saturated loss)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 2, 3, T, HW, HW, generator=g)
+    x = x + 1.5 * torch.randn(B, 2, 3, 1, 1, 1, generator=g)
+    ramp = torch.linspace(-1, 1, HW).view(1, 1, 1, 1, 1, HW)
+    return x + torch.randn(B, 2, 3, 1, 1, 1, generator=g) * ramp
+
+
+def compact(a, limit=16384):
+    """Large arrays are stored as a strided sample (every n-th element of the flattened array) + their L2 norm."""
+    a = np.asarray(a)
+    if a.size <= limit:
+        return a.copy(), None
+    stride = -(-a.size // limit)
+    return a.reshape(-1)[::stride].copy(), np.float64(np.linalg.norm(a.astype(np.float64)))
 
 
 GRAD_KEYS = ["encoder_q.0.Conv_1a.conv1.weight", "encoder_q.0.Conv_1a.bn2.weight", "encoder_q.0.Conv_2c.conv2.weight",
@@ -48,7 +67,14 @@ def import_reference():
     return mod
 
 
-def run_reference(K=128, B=4, T=8, ptr=16, threads=8):
+GRAD_KEYS_R50 = ["encoder_q.0.conv1.weight", "encoder_q.0.bn1.weight", "encoder_q.0.layer1.0.conv2.weight",
+                 "encoder_q.0.layer1.0.downsample.0.weight", "encoder_q.0.layer1.0.downsample.1.bias",
+                 "encoder_q.0.layer2.3.conv3.weight", "encoder_q.0.layer3.0.conv1.weight", "encoder_q.0.layer3.5.bn3.weight",
+                 "encoder_q.0.layer4.2.conv1.weight", "encoder_q.2.weight", "encoder_q.4.bias"]
+R50_CFG = dict(K=128, B=4, T=8, HW=64, ptr=16)     # BASELINE.json config 5 (--net r50) at a CPU-sized shape
+
+
+def run_reference(K=128, B=4, T=8, ptr=16, threads=8, network="s3d", HW=128):
     import torch.distributed as dist
     InfoNCE = import_reference().InfoNCE  # the unmodified reference
     from oracle import coclr_oracle as O
@@ -59,11 +85,11 @@ def run_reference(K=128, B=4, T=8, ptr=16, threads=8):
         os.environ.setdefault("MASTER_PORT", "29581")
         dist.init_process_group("gloo", rank=0, world_size=1)
     torch.manual_seed(0)
-    model = InfoNCE("s3d", 128, K, 0.999, 0.07)
-    sd = O.synth_state(O.infonce_shapes(128, K), seed=0, ptr=ptr)
+    model = InfoNCE(network, 128, K, 0.999, 0.07)
+    sd = O.synth_state(O.infonce_shapes(128, K, network=network), seed=0, ptr=ptr)
     model.load_state_dict(O.with_aliases(sd), strict=True)
     model.train()
-    block = make_inputs(B, T)
+    block = make_inputs(B, T, HW) if network == "s3d" else make_inputs_shifted(B, T, HW)
     torch.manual_seed(77)  # fixes the torch.randperm draw of _batch_shuffle_ddp (pretrain.py:112)
     logits, labels = model(block)
     loss = torch.nn.CrossEntropyLoss()(logits, labels)
@@ -71,8 +97,19 @@ def run_reference(K=128, B=4, T=8, ptr=16, threads=8):
     out = {"logits": logits.detach().numpy(), "loss": np.float64(loss.item()),
            "queue": model.queue.numpy().copy(), "queue_ptr": model.queue_ptr.numpy().copy()}
     named = dict(model.named_parameters())
-    for k in GRAD_KEYS:
-        out["grad/" + k] = named[k].grad.numpy().copy()
+    if network == "s3d":
+        for k in GRAD_KEYS:
+            out["grad/" + k] = named[k].grad.numpy().copy()
+    if network == "r50":
+        for k in GRAD_KEYS_R50:
+            out["grad/" + k], nrm = compact(named[k].grad.numpy())
+            if nrm is not None:
+                out["gradnorm/" + k] = nrm
+        full = model.state_dict()
+        out["ema/encoder_k.0.layer2.0.conv2.weight"] = named["encoder_k.0.layer2.0.conv2.weight"].detach().numpy().copy()
+        out["bn/encoder_q.0.layer1.0.downsample.1.running_mean"] = full["encoder_q.0.layer1.0.downsample.1.running_mean"].numpy().copy()
+        out["bn/encoder_k.0.layer4.2.bn3.running_var"] = full["encoder_k.0.layer4.2.bn3.running_var"].numpy().copy()
+        return out, model
     out["ema/encoder_k.0.Conv_2c.conv1.weight"] = named["encoder_k.0.Conv_2c.conv1.weight"].detach().numpy().copy()
     out["bn/encoder_q.0.Conv_1a.bn1.running_mean"] = model.state_dict()["encoder_q.0.Conv_1a.bn1.running_mean"].numpy().copy()
     out["bn/encoder_k.0.Mixed_5c.branch0.0.bn.running_var"] = model.state_dict()["encoder_k.0.Mixed_5c.branch0.0.bn.running_var"].numpy().copy()
@@ -80,6 +117,10 @@ def run_reference(K=128, B=4, T=8, ptr=16, threads=8):
 
 
 if __name__ == "__main__":
-    out, _ = run_reference()
-    np.savez_compressed(os.path.join(HERE, "infonce_cfg1.npz"), **out)
+    if "r50" in sys.argv[1:]:
+        out, _ = run_reference(network="r50", **R50_CFG)
+        np.savez_compressed(os.path.join(HERE, "infonce_r50.npz"), **out)
+    else:
+        out, _ = run_reference()
+        np.savez_compressed(os.path.join(HERE, "infonce_cfg1.npz"), **out)
     print("loss", out["loss"], "logits[0,:4]", out["logits"][0, :4])

@@ -80,3 +80,63 @@ def test_alias_expansion_covers_reference_keys():
     assert full["encoder_k.0.block5.2.branch3.1.bn.bias"] is sd["encoder_k.0.Mixed_5c.branch3.1.bn.bias"]
     # 235 parameter tensors per encoder, as the reference's named_parameters() reports
     assert len(O.param_keys(sd, "encoder_q.")) == 235
+
+
+# ---- r50 (ResNet2d3d-50, BASELINE.json config 5) -------------------------------------------------
+GOLD_R50 = os.path.join(ROOT, "tests", "golden", "infonce_r50.npz")
+
+
+def _oracle_step_r50():
+    c = MG.R50_CFG
+    sd = O.synth_state(O.infonce_shapes(128, c["K"], network="r50"), seed=0, ptr=c["ptr"])
+    for k in O.param_keys(sd, "encoder_q."):
+        sd[k].requires_grad_(True)
+    block = MG.make_inputs_shifted(c["B"], c["T"], c["HW"])
+    torch.manual_seed(77)
+    idx = torch.randperm(c["B"])
+    logits, labels = O.infonce_forward(sd, [block], idx)
+    loss = O.infonce_loss(logits[0], labels)
+    loss.backward()
+    return sd, logits[0], loss
+
+
+def test_oracle_r50_matches_golden():
+    gold = np.load(GOLD_R50)
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    sd, logits, loss = _oracle_step_r50()
+    assert logits.shape == (4, 129)
+    assert _rel(logits.detach().numpy(), gold["logits"]) < 2e-4
+    assert _rel(sd["queue"].numpy(), gold["queue"]) < 2e-4
+    assert int(sd["queue_ptr"]) == int(gold["queue_ptr"][0]) == 20
+    assert _rel(sd["encoder_k.0.layer2.0.conv2.weight"].detach().numpy(), gold["ema/encoder_k.0.layer2.0.conv2.weight"]) < 1e-6
+    assert _rel(sd["encoder_q.0.layer1.0.downsample.1.running_mean"].numpy(),
+                gold["bn/encoder_q.0.layer1.0.downsample.1.running_mean"]) < 1e-5
+    assert _rel(sd["encoder_k.0.layer4.2.bn3.running_var"].numpy(), gold["bn/encoder_k.0.layer4.2.bn3.running_var"]) < 1e-4
+    for k in MG.GRAD_KEYS_R50:
+        got, _ = MG.compact(sd[k].grad.numpy())
+        assert _rel(got, gold["grad/" + k]) < 5e-2, k
+
+
+def test_r50_inventory():
+    sh = O.r50_shapes("")
+    convs = [k for k, v in sh.items() if len(v) == 5]
+    assert len(convs) == 53
+    n_params = sum(int(np.prod(v)) for k, v in sh.items() if k.endswith(".weight") or k.endswith(".bias"))
+    assert n_params == 31_632_960 or abs(n_params - 31.7e6) < 0.2e6, n_params
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference not mounted")
+def test_oracle_r50_bitwise_vs_reference():
+    torch.set_num_threads(8)
+    out, model = MG.run_reference(threads=8, network="r50", **MG.R50_CFG)
+    sd, logits, loss = _oracle_step_r50()
+    assert np.array_equal(logits.detach().numpy(), out["logits"])
+    assert loss.item() == float(out["loss"])
+    assert np.array_equal(sd["queue"].numpy(), out["queue"])
+    named = dict(model.named_parameters())
+    for k in MG.GRAD_KEYS_R50:
+        assert _rel(sd[k].grad.numpy(), named[k].grad.numpy()) < 1e-6, k
+    msd = model.state_dict()
+    assert set(msd.keys()) == set(sd.keys())
+    for k, v in sd.items():
+        assert _rel(v.detach().numpy(), msd[k].numpy()) < 1e-6, k
