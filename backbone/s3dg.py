@@ -10,12 +10,7 @@ import torch
 import torch.nn as nn
 
 from coclr_b200.s3d_spec import s3d_stages, S3D_BLOCKS
-from coclr_b200.engine import Graph, ParamStore, EncoderEngine
-
-
-def _holder_forward(self, *a, **k):
-    raise RuntimeError("%s is a parameter holder; run the enclosing S3D / encoder module (CUDA only)"
-                       % type(self).__name__)
+from coclr_b200.backbone_base import EngineBackbone, holder_forward as _holder_forward
 
 
 class BasicConv3d(nn.Module):
@@ -78,7 +73,11 @@ class SepInception(nn.Module):
     forward = _holder_forward
 
 
-class S3D(nn.Module):
+class S3D(EngineBackbone):
+    """x: [B, C, T, H, W] -> [B, 1024, T/8, H/32, W/32] (reference s3dg.py:135-217)."""
+
+    _probe = "Conv_1a.conv1.weight"
+
     def __init__(self, input_channel=3, gating=False, slow=False, precision="parity"):
         super().__init__()
         if gating or slow:
@@ -104,27 +103,4 @@ class S3D(nn.Module):
         for blk, members in S3D_BLOCKS.items():
             if blk != "block1":
                 setattr(self, blk, nn.Sequential(*[getattr(self, m) for m in members]))
-        self._engine = None
-
-    # -- engine plumbing (standalone backbone use; inside a MoCo encoder the encoder owns the engine) --
-    def _get_engine(self):
-        w = self.Conv_1a.conv1.weight
-        if not w.is_cuda:
-            raise RuntimeError("coclr_b200 S3D runs on CUDA (sm_100a) only; move the module to the GPU")
-        if self._engine is None or self._engine.store.device != w.device or \
-                w.data_ptr() != self._engine.store.view("Conv_1a.conv1.weight").data_ptr():
-            graph = Graph(self._stages, self.input_channel, head_dim=None)
-            store = ParamStore(graph, w.device)
-            store.bind_module(dict(self.named_parameters()), dict(self.named_buffers()))
-            self._engine = EncoderEngine(store, graph, self.precision)
-        return self._engine
-
-    def forward(self, x):
-        """x: [B, C, T, H, W] -> [B, 1024, T/8, H/32, W/32] (inference-style use of the bare backbone;
-        training goes through the MoCo encoder which owns forward+backward)."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise RuntimeError("the bare S3D module is forward-only; wrap it in coclr_b200's MoCo encoder "
-                               "(model.pretrain) for training, or call under torch.no_grad()")
-        eng = self._get_engine()
-        plan = eng.forward(x.contiguous(), training=self.training, with_backward=False)
-        return eng.backbone_output_ncdhw(plan)
+        self._init_engine_state()

@@ -1,13 +1,17 @@
 """Backbone factory with the reference's signature (backbone/select_backbone.py:4-16)."""
 from .s3dg import S3D
+from .resnet_2d3d import r2d3d50
 
 
 def select_backbone(network, first_channel=3):
-    """-> (module, {'feature_size': int}). 's3d' runs on the sm_100a engine; other names of the reference
-    ('s3dg', 'r50') are not on the accelerated path yet and raise NotImplementedError like unknown names."""
+    """-> (module, {'feature_size': int}). 's3d' and 'r50' run on the sm_100a engine; 's3dg' (self-gating) is not on
+    the accelerated path and raises NotImplementedError like unknown names do in the reference."""
     param = {'feature_size': 1024}
     if network == 's3d':
         model = S3D(input_channel=first_channel)
+    elif network == 'r50':
+        param['feature_size'] = 2048
+        model = r2d3d50(input_channel=first_channel)
     else:
-        raise NotImplementedError("backbone %r is not available in coclr_b200 (supported: 's3d')" % (network,))
+        raise NotImplementedError("backbone %r is not available in coclr_b200 (supported: 's3d', 'r50')" % (network,))
     return model, param

@@ -19,7 +19,7 @@ EXPORTS = {
     "coclr_bias_relu_bwd": (I, [P, P, P, P, I, I, P]),
     "coclr_maxpool_fwd": (I, [P, P]),
     "coclr_maxpool_bwd": (I, [P, P]),
-    "coclr_avgpool_fwd": (I, [P, P, I, I, P, I, I, I, P]),
+    "coclr_avgpool_fwd": (I, [P, P, I, I, I, P, I, I, I, P]),
     "coclr_avgpool_bwd": (I, [P, P, I, I, I, I, I, P]),
     "coclr_pack_input": (I, [P, LG, LG, I, P, P, P, P, I, LG, P, P]),
     "coclr_pack_input_s2d": (I, [P, LG, LG, I, P, P, P, P, I, I, I, I, P, P]),

@@ -151,13 +151,20 @@ struct ConvSmemLayout {
   uint32_t total;
 };
 
+// per-warp BatchNorm statistic tables cover all output channels when those are few (flushed once per CTA), else one
+// N-tile (flushed after every tile: wide layers -- ResNet2d3d-50 has up to 2048 channels -- have few pixel tiles)
+static constexpr int kStatTableMaxCols = 512;
+__host__ __device__ inline int stat_table_cols(int BN, int n_tiles) {
+  return n_tiles * BN <= kStatTableMaxCols ? n_tiles * BN : BN;
+}
+
 __host__ __device__ inline ConvSmemLayout conv_smem_layout(int BN, int n_tiles, int npass, int want_stats) {
   ConvSmemLayout L;
   const uint32_t copies = npass > 1 ? 2u : 1u;
   L.a_bytes = kTileM * 128u;
   L.b_bytes = (uint32_t)BN * 128u;
   L.stage_bytes = copies * (L.a_bytes + L.b_bytes);
-  const uint32_t stat_bytes = want_stats ? kEpiWarps * 2u * (uint32_t)(n_tiles * BN + 4) * 4u : 0u;
+  const uint32_t stat_bytes = want_stats ? kEpiWarps * 2u * (uint32_t)(stat_table_cols(BN, n_tiles) + 4) * 4u : 0u;
   const uint32_t fixed = kEpiWarps * 32u * kStagePitch * 4u + stat_bytes + 256u;
   const uint32_t budget = 227u * 1024u - 1024u /*alignment slack*/ - fixed;
   uint32_t st = budget / L.stage_bytes;
@@ -184,7 +191,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
 
   float* stage_buf = reinterpret_cast<float*>(smem + L.off_stage);
   float* wstats = reinterpret_cast<float*>(smem + L.off_stats);
-  const int stat_cols = P.n_tiles * P.BN + 4;
+  const bool stats_per_tile = P.n_tiles * P.BN > kStatTableMaxCols;
+  const int stat_cols = stat_table_cols(P.BN, P.n_tiles) + 4;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.off_bars);  // [kMaxStages]
   uint64_t* empty_bar = full_bar + kMaxStages;                           // [kMaxStages]
   uint64_t* tfull_bar = empty_bar + kMaxStages;                          // [2]
@@ -378,10 +386,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
           }
           if (rg == 0 && colq < P.N) {
             float* ws = wstats + (size_t)warp * 2 * stat_cols;
+            const int tc = stats_per_tile ? c0 + cq * 4 : colq;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              ws[colq + k] += s1[k];
-              ws[stat_cols + colq + k] += s2[k];
+              ws[tc + k] += s1[k];
+              ws[stat_cols + tc + k] += s2[k];
             }
           }
         }
@@ -390,8 +399,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (stats_per_tile && P.stats_sum != nullptr) {
+        named_bar_sync(1, kEpiWarps * 32);
+        for (int c = threadIdx.x; c < P.BN; c += kEpiWarps * 32) {
+          double a = 0.0, b = 0.0;
+#pragma unroll
+          for (int w = 0; w < kEpiWarps; ++w) {
+            float* ws = wstats + (size_t)w * 2 * stat_cols;
+            a += (double)ws[c];
+            b += (double)ws[stat_cols + c];
+            ws[c] = 0.f;
+            ws[stat_cols + c] = 0.f;
+          }
+          if (n_tile * P.BN + c < P.N) {
+            atomicAdd(&P.stats_sum[n_tile * P.BN + c], a);
+            atomicAdd(&P.stats_sq[n_tile * P.BN + c], b);
+          }
+        }
+        named_bar_sync(1, kEpiWarps * 32);
+      }
     }
-    if (P.stats_sum != nullptr) {
+    if (P.stats_sum != nullptr && !stats_per_tile) {
       named_bar_sync(1, kEpiWarps * 32);
       for (int c = threadIdx.x; c < P.N; c += kEpiWarps * 32) {
         double a = 0.0, b = 0.0;

@@ -30,6 +30,27 @@ COCLR_DEVINL float4 ld_pair4(const uint16_t* hi, const uint16_t* lo, size_t off)
   return v;
 }
 
+COCLR_DEVINL float b2f(uint16_t h) { return __uint_as_float((uint32_t)h << 16); }
+
+// same for a run-time plane format (bf16 != 0: bf16 planes)
+COCLR_DEVINL float4 ld_pair4_any(const uint16_t* hi, const uint16_t* lo, size_t off, int bf16) {
+  if (!bf16) return ld_pair4(hi, lo, off);
+  const uint2 h = *reinterpret_cast<const uint2*>(hi + off);
+  float4 v;
+  v.x = b2f((uint16_t)(h.x & 0xffff));
+  v.y = b2f((uint16_t)(h.x >> 16));
+  v.z = b2f((uint16_t)(h.y & 0xffff));
+  v.w = b2f((uint16_t)(h.y >> 16));
+  if (lo != nullptr) {
+    const uint2 l = *reinterpret_cast<const uint2*>(lo + off);
+    v.x += b2f((uint16_t)(l.x & 0xffff));
+    v.y += b2f((uint16_t)(l.x >> 16));
+    v.z += b2f((uint16_t)(l.y & 0xffff));
+    v.w += b2f((uint16_t)(l.y >> 16));
+  }
+  return v;
+}
+
 template <bool kBf16>
 COCLR_DEVINL void st_pair4(uint16_t* hi, uint16_t* lo, size_t off, float4 v) {
   uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
@@ -95,6 +116,11 @@ __global__ void __launch_bounds__(256) affine_split_kernel(const coclr_split_t P
       v.z = fmaf(v.z, sc.z, sh.z);
       v.w = fmaf(v.w, sc.w, sh.w);
     }
+    if (P.res_hi != nullptr) {
+      const float4 rr = ld_pair4_any(reinterpret_cast<const uint16_t*>(P.res_hi), reinterpret_cast<const uint16_t*>(P.res_lo),
+                                     (size_t)(r * P.res_ld + P.res_coff + c), kBf16);
+      v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+    }
     if (P.relu) {
       v.x = fmaxf(v.x, 0.f);
       v.y = fmaxf(v.y, 0.f);
@@ -112,6 +138,7 @@ __global__ void __launch_bounds__(256) affine_split_kernel(const coclr_split_t P
 // column-reduce helper: thread t < A owns channel group (t % C4) and rows (t / C4) + k*(A / C4)
 // ------------------------------------------------------------------------------------------------
 static constexpr int kColThreads = 256;
+static constexpr int kMaxBnC = 2048;   // widest BatchNorm on the path: ResNet2d3d-50 layer4 (resnet_2d3d.py:146)
 
 // BatchNorm finalize fused with apply + ReLU + split: every block derives (scale, shift) of all channels into
 // shared memory from the statistics (cheap: C <= 1024), block 0 also publishes them (backward needs
@@ -119,7 +146,7 @@ static constexpr int kColThreads = 256;
 // affine_split_kernel.
 template <bool kBf16>
 __global__ void __launch_bounds__(256) bn_apply_split_kernel(const coclr_split_t P) {
-  __shared__ float s_sc[1024], s_sh[1024];
+  __shared__ float s_sc[kMaxBnC], s_sh[kMaxBnC];
   const coclr_bn_finalize_t& F = P.bn;
   for (int c = threadIdx.x; c < P.C; c += blockDim.x) {
     float mean, var;
@@ -164,6 +191,11 @@ __global__ void __launch_bounds__(256) bn_apply_split_kernel(const coclr_split_t
     v.y = fmaf(v.y, s_sc[c + 1], s_sh[c + 1]);
     v.z = fmaf(v.z, s_sc[c + 2], s_sh[c + 2]);
     v.w = fmaf(v.w, s_sc[c + 3], s_sh[c + 3]);
+    if (P.res_hi != nullptr) {
+      const float4 rr = ld_pair4_any(reinterpret_cast<const uint16_t*>(P.res_hi), reinterpret_cast<const uint16_t*>(P.res_lo),
+                                     (size_t)(r * P.res_ld + P.res_coff + c), kBf16);
+      v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+    }
     if (P.relu) {
       v.x = fmaxf(v.x, 0.f);
       v.y = fmaxf(v.y, 0.f);
@@ -177,27 +209,61 @@ __global__ void __launch_bounds__(256) bn_apply_split_kernel(const coclr_split_t
   }
 }
 
-// BN backward, phase 1: s1[c] = sum dz, s2[c] = sum dz * xhat, dz = dA * [scale*y+shift > 0]
+// BN backward.  Channel tiles of <= kBwdTileC channels on blockIdx.y (ResNet2d3d-50 has up to 2048 channels), row
+// slabs on blockIdx.x.  With a residual (P.res_hi) the unit is relu(bn(y) + r): r enters the ReLU mask and dz is also
+// the residual branch's gradient.
+static constexpr int kBwdTileC = 1024;
+
+struct BwdCols {
+  int C4, A, R, cb;   // float4 column groups of this tile, active threads, rows per pass, first channel of the tile
+};
+COCLR_DEVINL BwdCols bwd_cols(const coclr_bn_bwd_t& P) {
+  BwdCols k;
+  k.cb = blockIdx.y * kBwdTileC;
+  const int Cl = min(P.C - k.cb, kBwdTileC);
+  k.C4 = Cl >> 2;
+  k.A = (kColThreads / k.C4) * k.C4;
+  k.R = k.A / k.C4;
+  return k;
+}
+
+COCLR_DEVINL float4 bwd_dz(const coclr_bn_bwd_t& P, size_t row, int cc, const float4& y, const float4& da, const float4& sc,
+                           const float4& sh) {
+  if (!P.relu) return da;
+  float4 z;
+  z.x = fmaf(y.x, sc.x, sh.x);
+  z.y = fmaf(y.y, sc.y, sh.y);
+  z.z = fmaf(y.z, sc.z, sh.z);
+  z.w = fmaf(y.w, sc.w, sh.w);
+  if (P.res_hi != nullptr) {
+    const float4 rr = ld_pair4_any(reinterpret_cast<const uint16_t*>(P.res_hi), reinterpret_cast<const uint16_t*>(P.res_lo),
+                                   row * (size_t)P.res_ld + P.res_coff + cc, P.res_bf16);
+    z.x += rr.x; z.y += rr.y; z.z += rr.z; z.w += rr.w;
+  }
+  float4 dz;
+  dz.x = z.x > 0.f ? da.x : 0.f;
+  dz.y = z.y > 0.f ? da.y : 0.f;
+  dz.z = z.z > 0.f ? da.z : 0.f;
+  dz.w = z.w > 0.f ? da.w : 0.f;
+  return dz;
+}
+
+// phase 1: s1[c] = sum dz, s2[c] = sum dz * xhat, dz = dA * [scale*y+shift (+ r) > 0]
 __global__ void __launch_bounds__(kColThreads) bn_bwd_reduce_kernel(const coclr_bn_bwd_t P) {
-  const int C4 = P.C >> 2;
-  const int A = (kColThreads / C4) * C4;
-  const int R = A / C4;
+  const BwdCols K = bwd_cols(P);
+  const int C4 = K.C4, A = K.A, R = K.R;
   __shared__ float red[8][kColThreads];
   const int t = threadIdx.x;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (t < A) {
     const int cg = t % C4, rs = t / C4;
-    const int c = cg * 4;
+    const int c = K.cb + cg * 4;
     const float4 sc = ld4(P.scale + c), sh = ld4(P.shift + c), mu = ld4(P.mean + c), rs4 = ld4(P.rstd + c);
     const long rows_per = ((long)P.M + gridDim.x - 1) / gridDim.x;
     const long r_begin = (long)blockIdx.x * rows_per;
     const long r_end = min((long)P.M, r_begin + rows_per);
-    auto body = [&](const float4& y, const float4& da) {
-      float4 dz;
-      dz.x = (!P.relu || fmaf(y.x, sc.x, sh.x) > 0.f) ? da.x : 0.f;
-      dz.y = (!P.relu || fmaf(y.y, sc.y, sh.y) > 0.f) ? da.y : 0.f;
-      dz.z = (!P.relu || fmaf(y.z, sc.z, sh.z) > 0.f) ? da.z : 0.f;
-      dz.w = (!P.relu || fmaf(y.w, sc.w, sh.w) > 0.f) ? da.w : 0.f;
+    auto body = [&](long row, const float4& y, const float4& da) {
+      const float4 dz = bwd_dz(P, (size_t)row, c, y, da, sc, sh);
       acc[0] += dz.x; acc[1] += dz.y; acc[2] += dz.z; acc[3] += dz.w;
       acc[4] += dz.x * ((y.x - mu.x) * rs4.x);
       acc[5] += dz.y * ((y.y - mu.y) * rs4.y);
@@ -213,9 +279,9 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_reduce_kernel(const coclr_
         da[u] = ld4(P.dA + (r + u * R) * P.ld + P.coff + c);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) body(y[u], da[u]);
+      for (int u = 0; u < 4; ++u) body(r + u * R, y[u], da[u]);
     }
-    for (; r < r_end; r += R) body(ld4(P.y + r * P.ld + P.coff + c), ld4(P.dA + r * P.ld + P.coff + c));
+    for (; r < r_end; r += R) body(r, ld4(P.y + r * P.ld + P.coff + c), ld4(P.dA + r * P.ld + P.coff + c));
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) red[j][t] = acc[j];
@@ -227,22 +293,21 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_reduce_kernel(const coclr_
       for (int j = 0; j < 8; ++j) s[j] += (double)red[j][t + k * C4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      atomicAdd(P.sums + t * 4 + j, s[j]);
-      atomicAdd(P.sums + P.C + t * 4 + j, s[4 + j]);
+      atomicAdd(P.sums + K.cb + t * 4 + j, s[j]);
+      atomicAdd(P.sums + P.C + K.cb + t * 4 + j, s[4 + j]);
     }
   }
 }
 
-// BN backward, phase 2: dY = scale * (dz - s1/n - xhat * s2/n) -> bf16 hi/lo planes; block 0 also
+// phase 2: dY = scale * (dz - s1/n - xhat * s2/n) -> bf16 hi/lo planes; dres (+)= dz; the first row slab also
 // accumulates dgamma += s2, dbeta += s1.
 __global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(const coclr_bn_bwd_t P) {
-  const int C4 = P.C >> 2;
-  const int A = (kColThreads / C4) * C4;
-  const int R = A / C4;
+  const BwdCols K = bwd_cols(P);
+  const int C4 = K.C4, A = K.A, R = K.R;
   const int t = threadIdx.x;
   if (t >= A) return;
   const int cg = t % C4, rs = t / C4;
-  const int c = cg * 4;
+  const int c = K.cb + cg * 4;
   const float4 sc = ld4(P.scale + c), sh = ld4(P.shift + c), mu = ld4(P.mean + c), rs4 = ld4(P.rstd + c);
   const double inv_n = 1.0 / (double)P.M;
   float m1[4], m2[4];
@@ -261,25 +326,23 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(const coclr_b
   const long rows_per = ((long)P.M + gridDim.x - 1) / gridDim.x;
   const long r_begin = (long)blockIdx.x * rows_per;
   const long r_end = min((long)P.M, r_begin + rows_per);
-  auto body = [&](size_t off, const float4& y, const float4& da) {
+  auto body = [&](long row, size_t off, const float4& y, const float4& da) {
+    const float4 dz = bwd_dz(P, (size_t)row, c, y, da, sc, sh);
     float4 o;
-    {
-      const float dz = (!P.relu || fmaf(y.x, sc.x, sh.x) > 0.f) ? da.x : 0.f;
-      o.x = sc.x * (dz - m1[0] - ((y.x - mu.x) * rs4.x) * m2[0]);
-    }
-    {
-      const float dz = (!P.relu || fmaf(y.y, sc.y, sh.y) > 0.f) ? da.y : 0.f;
-      o.y = sc.y * (dz - m1[1] - ((y.y - mu.y) * rs4.y) * m2[1]);
-    }
-    {
-      const float dz = (!P.relu || fmaf(y.z, sc.z, sh.z) > 0.f) ? da.z : 0.f;
-      o.z = sc.z * (dz - m1[2] - ((y.z - mu.z) * rs4.z) * m2[2]);
-    }
-    {
-      const float dz = (!P.relu || fmaf(y.w, sc.w, sh.w) > 0.f) ? da.w : 0.f;
-      o.w = sc.w * (dz - m1[3] - ((y.w - mu.w) * rs4.w) * m2[3]);
-    }
+    o.x = sc.x * (dz.x - m1[0] - ((y.x - mu.x) * rs4.x) * m2[0]);
+    o.y = sc.y * (dz.y - m1[1] - ((y.y - mu.y) * rs4.y) * m2[1]);
+    o.z = sc.z * (dz.z - m1[2] - ((y.z - mu.z) * rs4.z) * m2[2]);
+    o.w = sc.w * (dz.w - m1[3] - ((y.w - mu.w) * rs4.w) * m2[3]);
     st_pair4<true>(hi, lo, off, o);
+    if (P.dres != nullptr) {
+      float* d = P.dres + (size_t)row * P.dres_ld + P.dres_coff + c;
+      float4 v = dz;
+      if (P.dres_accumulate) {
+        const float4 old = ld4(d);
+        v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+      }
+      st4(d, v);
+    }
   };
   long r = r_begin + rs;
   for (; r + 3 * R < r_end; r += 4 * R) {
@@ -292,11 +355,11 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(const coclr_b
       da[u] = ld4(P.dA + off[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) body(off[u], y[u], da[u]);
+    for (int u = 0; u < 4; ++u) body(r + u * R, off[u], y[u], da[u]);
   }
   for (; r < r_end; r += R) {
     const size_t off = (size_t)(r * P.ld + P.coff + c);
-    body(off, ld4(P.y + off), ld4(P.dA + off));
+    body(r, off, ld4(P.y + off), ld4(P.dA + off));
   }
 }
 
@@ -589,8 +652,8 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const coclr_pool_t P) 
 // ------------------------------------------------------------------------------------------------
 // AdaptiveAvgPool3d((1,1,1)) (model/pretrain.py:51) over fp16 hi/lo planes, and its backward
 // ------------------------------------------------------------------------------------------------
-__global__ void avgpool_fwd_kernel(const uint16_t* xh, const uint16_t* xl, int ld, int coff, float* out, int B, int Pn,
-                                   int C) {
+__global__ void avgpool_fwd_kernel(const uint16_t* xh, const uint16_t* xl, int bf16, int ld, int coff, float* out, int B,
+                                   int Pn, int C) {
   const int C4 = C >> 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C4) return;
@@ -598,7 +661,7 @@ __global__ void avgpool_fwd_kernel(const uint16_t* xh, const uint16_t* xl, int l
   const int c = cg * 4;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int p = 0; p < Pn; ++p) {
-    const float4 v = ld_pair4(xh, xl, ((size_t)b * Pn + p) * ld + coff + c);
+    const float4 v = ld_pair4_any(xh, xl, ((size_t)b * Pn + p) * ld + coff + c, bf16);
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
   const float inv = 1.f / (float)Pn;
@@ -790,10 +853,11 @@ extern "C" int coclr_bn_finalize(const coclr_bn_finalize_t* p, coclr_stream_t st
 extern "C" int coclr_affine_split(const coclr_split_t* p, int num_sms, coclr_stream_t stream) {
   if (!p || !p->x || !p->hi || p->C % 4 || p->ld % 4 || p->coff % 4 || p->out_ld % 4 || p->out_coff % 4)
     return COCLR_E_ARG;
+  if (p->res_hi && (p->res_ld % 4 || p->res_coff % 4)) return COCLR_E_ARG;
   const long total = p->M * (p->C / 4);
   if (p->bn.scale != nullptr) {  // fused BatchNorm finalize
     const coclr_bn_finalize_t& f = p->bn;
-    if (!f.shift || !f.gamma || !f.beta || !f.running_mean || !f.running_var || p->C > 1024) return COCLR_E_ARG;
+    if (!f.shift || !f.gamma || !f.beta || !f.running_mean || !f.running_var || p->C > kMaxBnC) return COCLR_E_ARG;
     if (f.training && (!f.sum || !f.sumsq || f.count <= 0)) return COCLR_E_ARG;
     const int grid = grid_for(total, 256, num_sms * 16);
     if (p->bf16)
@@ -811,13 +875,18 @@ extern "C" int coclr_affine_split(const coclr_split_t* p, int num_sms, coclr_str
 }
 
 extern "C" int coclr_bn_bwd(const coclr_bn_bwd_t* p, int num_sms, coclr_stream_t stream) {
-  if (!p || !p->y || !p->dA || !p->sums || !p->dy_hi || p->C % 4 || p->C > 1024 || p->ld % 4 || p->coff % 4)
-    return COCLR_E_ARG;
-  const int C4 = p->C / 4;
+  if (!p || !p->y || !p->dA || !p->sums || !p->dy_hi || p->C % 4 || p->ld % 4 || p->coff % 4) return COCLR_E_ARG;
+  if (p->res_hi && (p->res_ld % 4 || p->res_coff % 4 || !p->relu)) return COCLR_E_ARG;
+  if (p->dres && (p->dres_ld % 4 || p->dres_coff % 4)) return COCLR_E_ARG;
+  const int ctiles = (p->C + kBwdTileC - 1) / kBwdTileC;
+  if (ctiles > 1 && p->C % kBwdTileC) return COCLR_E_ARG;   // wide tensors: whole tiles only
+  const int C4 = (ctiles > 1 ? kBwdTileC : p->C) / 4;
   const int R = kColThreads / C4;
   long slabs = ((long)p->M + (long)R * 16 - 1) / ((long)R * 16);
-  int grid = (int)(slabs < (long)num_sms * 8 ? slabs : (long)num_sms * 8);
-  if (grid < 1) grid = 1;
+  const long cap = (long)num_sms * 8 / ctiles;
+  int gx = (int)(slabs < cap ? slabs : cap);
+  if (gx < 1) gx = 1;
+  const dim3 grid(gx, ctiles);
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(p->sums, 0, sizeof(double) * 2 * p->C, s) != cudaSuccess) return COCLR_E_LAUNCH;
   bn_bwd_reduce_kernel<<<grid, kColThreads, 0, s>>>(*p);
@@ -888,11 +957,11 @@ extern "C" int coclr_maxpool_bwd(const coclr_pool_t* p, coclr_stream_t stream) {
   return LAUNCH_OK();
 }
 
-extern "C" int coclr_avgpool_fwd(const void* x_hi, const void* x_lo, int ld, int coff, float* out, int B, int Pn, int C,
-                                 coclr_stream_t stream) {
+extern "C" int coclr_avgpool_fwd(const void* x_hi, const void* x_lo, int bf16, int ld, int coff, float* out, int B, int Pn,
+                                 int C, coclr_stream_t stream) {
   if (!x_hi || !out || C % 4) return COCLR_E_ARG;
   avgpool_fwd_kernel<<<(B * (C / 4) + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint16_t*>(x_hi), reinterpret_cast<const uint16_t*>(x_lo), ld, coff, out, B, Pn, C);
+      reinterpret_cast<const uint16_t*>(x_hi), reinterpret_cast<const uint16_t*>(x_lo), bf16, ld, coff, out, B, Pn, C);
   return LAUNCH_OK();
 }
 extern "C" int coclr_avgpool_bwd(const float* dfeat, float* dA, int ld, int coff, int B, int Pn, int C,

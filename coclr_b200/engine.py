@@ -43,6 +43,7 @@ class TensorSpec:
         self.name, self.C, self.dims_fn, self.pending = name, C, dims_fn, pending
         self.bn_members = []   # (bn module name, coff, C) in channel order
         self.relu = 1 if pending else 0
+        self.residual = None   # TensorSpec added before the ReLU (ResNet bottleneck output)
 
 
 class ConvSpec:
@@ -96,8 +97,13 @@ class Graph:
         st0 = stages[0]
         # stride-2 7x7 RGB stem as a stride-1 4x4 conv over a space-to-depth input (16 channels / pixel): 16 taps of
         # 32-byte granules instead of 49 taps of 16-byte granules
-        self.stem_s2d = bool(stem_s2d and st0[0] == "st" and st0[4] == 7 and st0[5] == 2 and st0[7] == 3
-                             and 4 * first_channel <= 16)
+        if st0[0] == "st":
+            s2d_ok = st0[4] == 7 and st0[5] == 2 and st0[7] == 3
+        elif st0[0] == "convbn":
+            s2d_ok = tuple(st0[5][1:]) == (7, 7) and tuple(st0[6][1:]) == (2, 2) and tuple(st0[7][1:]) == (3, 3)
+        else:
+            s2d_ok = False
+        self.stem_s2d = bool(stem_s2d and s2d_ok and 4 * first_channel <= 16)
         if self.stem_s2d:
             x = self._tensor("input", 16, lambda d: (d[0], d[1] // 2, d[2] // 2), pending=False)
         else:
@@ -120,6 +126,26 @@ class Graph:
             elif kind == "pool":
                 _, name, k, s, p = stg
                 x = self._pool(pre + name, x, k, s, p)
+            elif kind == "convbn":
+                _, cname, bname, cin, cout, k, s, p = stg
+                s2d = first_conv and self.stem_s2d and x is self.input
+                if s2d:
+                    f = x.dims_fn
+                    dims = (lambda d, f=f, k=k, s=s, p=p: (_conv_out(f(d)[0], k[0], s[0], p[0]), f(d)[1], f(d)[2]))
+                else:
+                    dims = self._after(x, k, s, p)
+                y = self._tensor(pre + cname + ".out", cout, dims)
+                cv = self._conv(pre + cname, x, y, 0, cin, cout, tuple(k), tuple(s), tuple(p), need_dgrad=not first_conv)
+                if s2d:
+                    cv.s2d, cv.cin_eff = True, 4 * cin
+                    cv.k_eff, cv.s_eff, cv.p_eff = (k[0], 4, 4), (s[0], 1, 1), (p[0], 2, 2)
+                first_conv = False
+                y.bn_members.append((pre + bname, 0, cout))
+                self.items.append(("bn", y))
+                x = y
+            elif kind == "bottleneck":
+                _, name, inplanes, planes, stride, is3d, has_ds = stg
+                x = self._bottleneck(pre + name, x, inplanes, planes, stride, is3d, has_ds)
             elif kind == "mixed":
                 _, name, cin, planes = stg
                 x = self._mixed(pre + name, x, cin, planes)
@@ -198,6 +224,35 @@ class Graph:
         self.cur_lane, self.next_flag = 0, JOIN
         self.items.append(("bn", cat))
         return cat
+
+    def _bottleneck(self, name, x, inplanes, planes, stride, is3d, has_ds):
+        """Bottleneck2d / Bottleneck3d (backbone/resnet_2d3d.py:46-131): conv1 (1x1x1 or (3,1,1)) -> conv2 (1,3,3) with
+        the spatial stride -> conv3 1x1x1 (x4); out = relu(bn3(.) + residual), residual = x or bn(downsample conv(x))."""
+        one = ((1, 1, 1), (1, 1, 1), (0, 0, 0))
+        k1, s1, p1 = ((3, 1, 1), (1, 1, 1), (1, 0, 0)) if is3d else one
+        t1 = self._tensor(name + ".t1", planes, self._after(x, k1, s1, p1))
+        self._conv(name + ".conv1", x, t1, 0, inplanes, planes, k1, s1, p1)
+        t1.bn_members.append((name + ".bn1", 0, planes))
+        self.items.append(("bn", t1))
+        k2, s2, p2 = (1, 3, 3), (1, stride, stride), (0, 1, 1)
+        t2 = self._tensor(name + ".t2", planes, self._after(t1, k2, s2, p2))
+        self._conv(name + ".conv2", t1, t2, 0, planes, planes, k2, s2, p2)
+        t2.bn_members.append((name + ".bn2", 0, planes))
+        self.items.append(("bn", t2))
+        out = self._tensor(name, 4 * planes, self._same(t2))
+        self._conv(name + ".conv3", t2, out, 0, planes, 4 * planes, *one)
+        out.bn_members.append((name + ".bn3", 0, 4 * planes))
+        if has_ds:
+            ds = self._tensor(name + ".ds", 4 * planes, self._same(t2))
+            ds.relu = 0
+            self._conv(name + ".downsample.0", x, ds, 0, inplanes, 4 * planes, (1, 1, 1), (1, stride, stride), (0, 0, 0))
+            ds.bn_members.append((name + ".downsample.1", 0, 4 * planes))
+            self.items.append(("bn", ds))
+            out.residual = ds
+        else:
+            out.residual = x
+        self.items.append(("bn", out))
+        return out
 
     # -- parameter inventory (names relative to the encoder: backbone under bb_prefix, head '2.', '4.') --
     def param_layout(self):
@@ -357,11 +412,13 @@ class Plan:
                 return None, None
             return L.dptr(plw.hi), L.dptr(plw.lo)
 
-        def split_op(x, planes, M, Cc, scale, shift, relu, twin=None, bn=None):
+        def split_op(x, planes, M, Cc, scale, shift, relu, twin=None, bn=None, res=None):
             t_hi, t_lo = twin_ptrs(planes, twin)
             sp = L.Split(L.dptr(x), x.shape[-1], 0, Cc, M, L.dptr(scale), L.dptr(shift), int(bool(relu)),
                          L.dptr(planes.hi), L.dptr(planes.lo), planes.ld, 0, planes.bf16, t_hi, t_lo,
-                         bn if bn is not None else L.BnFinalize())
+                         bn if bn is not None else L.BnFinalize(),
+                         L.dptr(res.hi) if res is not None else None, L.dptr(res.lo) if res is not None else None,
+                         res.ld if res is not None else 0, 0)
             self.keep.append(sp)
             return (lib.coclr_affine_split, (C.byref(sp), nsm))
 
@@ -401,7 +458,8 @@ class Plan:
                                   BN_MOMENTUM, BN_EPS, int(training), L.dptr(a.scale), L.dptr(a.shift),
                                   L.dptr(a.mean), L.dptr(a.rstd), it.C)
                 # BatchNorm finalize is fused into the apply+split launch
-                self.fwd.append(split_op(a.data, a.pl, a.M, it.C, None, None, it.relu, a.plw, bn=bf))
+                res = acts[it.residual.index].pl if it.residual is not None else None
+                self.fwd.append(split_op(a.data, a.pl, a.M, it.C, None, None, it.relu, a.plw, bn=bf, res=res))
             for j in range(n_before, len(self.fwd)):     # tag the launches of this item with its lane / fork / join
                 self.fwd_lane[j] = (g.item_lane[item_i], g.item_flag[item_i] if j == n_before else 0)
         # ---- head ----
@@ -422,7 +480,7 @@ class Plan:
             mk_twin = with_backward and not fbf
             self.feat_plw = ops.Planes((B, 1, 1, 1, fs), 1, dev, lo=bnp > 1) if mk_twin else self.feat_pl
             self.h1_plw = ops.Planes((B, 1, 1, 1, fs), 1, dev, lo=bnp > 1) if mk_twin else self.h1_pl
-            self.fwd.append((lib.coclr_avgpool_fwd, (L.dptr(out.pl.hi), L.dptr(out.pl.lo), out.spec.C, 0,
+            self.fwd.append((lib.coclr_avgpool_fwd, (L.dptr(out.pl.hi), L.dptr(out.pl.lo), out.pl.bf16, out.spec.C, 0,
                                                      L.dptr(self.feat), B, Pn, fs)))
             self.fwd.append(split_op(self.feat, self.feat_pl, B, fs, None, None, False, self.feat_plw))
             one = ops.Geometry((1, 1, 1))
@@ -487,9 +545,16 @@ class Plan:
                 first = t.bn_members[0][0]
                 goff = st.offsets[first + ".weight"][0]
                 boff_b = st.offsets[first + ".bias"][0]
+                if t.residual is not None:
+                    ra = acts[t.residual.index]
+                    res_args = (L.dptr(ra.pl.hi), L.dptr(ra.pl.lo), ra.pl.ld, 0, ra.pl.bf16,
+                                L.dptr(ra.grad), ra.spec.C, 0, int(ra.grad_written))
+                    ra.grad_written = True
+                else:
+                    res_args = (None, None, 0, 0, 0, None, 0, 0, 0)
                 bb = L.BnBwd(L.dptr(a.data), L.dptr(a.grad), t.C, 0, t.C, a.M, L.dptr(a.scale), L.dptr(a.shift),
                              L.dptr(a.mean), L.dptr(a.rstd), t.relu, L.dptr(a.bsums),
-                             L.dptr(st.grad[goff:]), L.dptr(st.grad[boff_b:]), L.dptr(a.dy.hi), L.dptr(a.dy.lo))
+                             L.dptr(st.grad[goff:]), L.dptr(st.grad[boff_b:]), L.dptr(a.dy.hi), L.dptr(a.dy.lo), *res_args)
                 self.keep.append(bb)
                 bw.append((lib.coclr_bn_bwd, (C.byref(bb), nsm)))
                 for it in convs_into[t.index]:
@@ -573,12 +638,13 @@ class EncoderEngine:
                 self._packs += [(pf, w, False), (pb, w, True)]
 
     def _make_s2d(self, it, w, dev):
-        """Index map of the space-to-depth stem: W'[o, (dy*2+dx)*Cin + c, 0, ty, tx] = W[o, c, 0, 2ty+dy-1, 2tx+dx-1]
+        """Index map of the space-to-depth stem: W'[o, (dy*2+dx)*Cin + c, t, ty, tx] = W[o, c, t, 2ty+dy-1, 2tx+dx-1]
         (zero when an index is -1).  Returns the persistent W' tensor that is re-derived before every packing."""
-        cout, cin = it.cout, it.cin
-        idx = torch.zeros(cout, 4 * cin, 1, 4, 4, dtype=torch.long)
-        msk = torch.zeros(cout, 4 * cin, 1, 4, 4, dtype=torch.float32)
+        cout, cin, kt = it.cout, it.cin, it.k[0]
+        idx = torch.zeros(cout, 4 * cin, kt, 4, 4, dtype=torch.long)
+        msk = torch.zeros(cout, 4 * cin, kt, 4, 4, dtype=torch.float32)
         o = torch.arange(cout).view(-1, 1)
+        t = torch.arange(kt).view(1, -1)
         for dy in range(2):
             for dx in range(2):
                 for ty in range(4):
@@ -587,11 +653,11 @@ class EncoderEngine:
                         if ky < 0 or kx < 0:
                             continue
                         for c in range(cin):
-                            idx[:, (dy * 2 + dx) * cin + c, 0, ty, tx] = ((o[:, 0] * cin + c) * 7 + ky) * 7 + kx
-                            msk[:, (dy * 2 + dx) * cin + c, 0, ty, tx] = 1.0
+                            idx[:, (dy * 2 + dx) * cin + c, :, ty, tx] = (((o * cin + c) * kt + t) * 7 + ky) * 7 + kx
+                            msk[:, (dy * 2 + dx) * cin + c, :, ty, tx] = 1.0
         d = {"idx": idx.to(dev).view(-1), "mask": msk.to(dev).view(-1), "w": w,
-             "w_eff": torch.zeros(cout, 4 * cin, 1, 4, 4, device=dev),
-             "dw_eff": torch.zeros(cout, 4 * cin, 1, 4, 4, device=dev),
+             "w_eff": torch.zeros(cout, 4 * cin, kt, 4, 4, device=dev),
+             "dw_eff": torch.zeros(cout, 4 * cin, kt, 4, 4, device=dev),
              "dw": self.store.view(it.name + ".weight", grad=True)}
         if not hasattr(self, "s2d"):
             self.s2d = {}

@@ -65,7 +65,8 @@ class Split(C.Structure):
     _fields_ = [("x", C.c_void_p), ("ld", C.c_int), ("coff", C.c_int), ("C", C.c_int), ("M", C.c_long),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int),
                 ("hi", C.c_void_p), ("lo", C.c_void_p), ("out_ld", C.c_int), ("out_coff", C.c_int),
-                ("bf16", C.c_int), ("hi2", C.c_void_p), ("lo2", C.c_void_p), ("bn", BnFinalize)]
+                ("bf16", C.c_int), ("hi2", C.c_void_p), ("lo2", C.c_void_p), ("bn", BnFinalize),
+                ("res_hi", C.c_void_p), ("res_lo", C.c_void_p), ("res_ld", C.c_int), ("res_coff", C.c_int)]
 
 
 class BnBwd(C.Structure):
@@ -73,7 +74,10 @@ class BnBwd(C.Structure):
                 ("M", C.c_long), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("mean", C.c_void_p), ("rstd", C.c_void_p), ("relu", C.c_int),
                 ("sums", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
-                ("dy_hi", C.c_void_p), ("dy_lo", C.c_void_p)]
+                ("dy_hi", C.c_void_p), ("dy_lo", C.c_void_p),
+                ("res_hi", C.c_void_p), ("res_lo", C.c_void_p), ("res_ld", C.c_int), ("res_coff", C.c_int),
+                ("res_bf16", C.c_int), ("dres", C.c_void_p), ("dres_ld", C.c_int), ("dres_coff", C.c_int),
+                ("dres_accumulate", C.c_int)]
 
 
 class Pool(C.Structure):

@@ -148,6 +148,11 @@ typedef struct {
    * (bn.training) or the running stats, written to bn.scale/bn.shift/bn.save_* and the running stats are updated
    * by one block -- saves the separate coclr_bn_finalize launch; `scale`/`shift` above are then ignored */
   coclr_bn_finalize_t bn;
+  /* optional residual branch of a ResNet bottleneck (`out += residual` then ReLU, backbone/resnet_2d3d.py:75-80,
+   * 118-123): operand planes of the same 16-bit format as hi/lo, added after the affine and before the ReLU */
+  const void* res_hi; /* NULL: no residual */
+  const void* res_lo; /* may be NULL */
+  int res_ld, res_coff;
 } coclr_split_t;
 int coclr_affine_split(const coclr_split_t* p, int num_sms, coclr_stream_t stream);
 
@@ -170,6 +175,13 @@ typedef struct {
   float* dbeta;
   void* dy_hi;    /* bf16 planes [M, ld] (same ld / coff as y) */
   void* dy_lo;    /* may be NULL */
+  /* residual block output (relu(bn(y) + r), backbone/resnet_2d3d.py:75-80): r's forward planes enter the ReLU mask,
+   * and dz = dA*[bn(y)+r > 0] is also the gradient of the residual branch, written (=) or added (+=) to dres */
+  const void* res_hi; /* NULL: plain BN(+ReLU) */
+  const void* res_lo;
+  int res_ld, res_coff, res_bf16;
+  float* dres; /* fp32 [M, dres_ld] at dres_coff, or NULL */
+  int dres_ld, dres_coff, dres_accumulate;
 } coclr_bn_bwd_t;
 int coclr_bn_bwd(const coclr_bn_bwd_t* p, int num_sms, coclr_stream_t stream);
 
@@ -199,7 +211,7 @@ int coclr_maxpool_fwd(const coclr_pool_t* p, coclr_stream_t stream);
 int coclr_maxpool_bwd(const coclr_pool_t* p, coclr_stream_t stream);
 
 /* ---- nn.AdaptiveAvgPool3d((1,1,1)) (model/pretrain.py:51) ---------------------------------------- */
-int coclr_avgpool_fwd(const void* x_hi, const void* x_lo, int ld, int coff, float* out, int B, int Pn, int C,
+int coclr_avgpool_fwd(const void* x_hi, const void* x_lo, int bf16 /* plane format */, int ld, int coff, float* out, int B, int Pn, int C,
                       coclr_stream_t stream);
 int coclr_avgpool_bwd(const float* dfeat, float* dA, int ld, int coff, int B, int Pn, int C, coclr_stream_t stream);
 

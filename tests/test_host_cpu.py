@@ -117,7 +117,7 @@ def test_launch_plans_build_on_cpu_dry_run():
         assert names.count("coclr_maxpool_fwd") == 13
         assert names.count("coclr_affine_split") == (77 - 9 * 3) + 2   # one fused BN-finalize+apply+split per tensor (concat tensors hold 4 BNs) + 2 head splits
         bn = [fn.__name__ for fn, _ in p.bwd]
-        assert bn.count("coclr_conv_wgrad") == 77 + 2
+        assert bn.count("coclr_conv_wgrad") + bn.count("coclr_conv_wgrad_s2d") == 77 + 2   # the stem's runs in space-to-depth form
         assert bn.count("coclr_conv_igemm") == 76 + 2           # no dgrad for the RGB stem conv
         assert bn.count("coclr_maxpool_bwd") == 13
         assert bn.count("coclr_bn_bwd") == 77 - 9 * 3
@@ -126,5 +126,36 @@ def test_launch_plans_build_on_cpu_dry_run():
         assert not p2.bwd and all(a.grad is None for a in p2.acts.values())
         # flat layout: every BN group contiguous, every offset 16-byte aligned
         assert all(off % 4 == 0 for off, _, _ in st.offsets.values())
+    finally:
+        L.DRY_RUN = False
+
+
+def test_r50_plan_structure_dry_run():
+    """ResNet2d3d-50 launch lists: 53 backbone convs, residual wiring, gradient coverage."""
+    from coclr_b200 import lib as L
+    from coclr_b200.engine import Graph, ParamStore, EncoderEngine
+    from coclr_b200.r50_spec import r50_stages
+    from oracle import coclr_oracle as O
+    L.DRY_RUN = True
+    try:
+        g = Graph(r50_stages(3), 3, head_dim=128, feature_size=2048, bb_prefix="0.")
+        assert g.stem_s2d
+        st = ParamStore(g, torch.device("cpu"))
+        want = {k[len("encoder_q."):]: tuple(v) for k, v in O.infonce_shapes(128, 128, network="r50").items()
+                if k.startswith("encoder_q.") and (k.endswith(".weight") or k.endswith(".bias"))}
+        assert {k: tuple(v[2]) for k, v in st.offsets.items()} == want
+        eng = EncoderEngine(st, g, "parity")
+        p = eng.plan(2, 8, 64, 64, True, True)
+        assert p.backbone_out.dims == (4, 2, 2) and p.backbone_out.spec.C == 2048
+        names = [fn.__name__ for fn, _ in p.fwd]
+        assert names.count("coclr_conv_igemm") == 53 + 2
+        assert names.count("coclr_maxpool_fwd") == 1
+        assert names.count("coclr_affine_split") == 53 + 2
+        bn = [fn.__name__ for fn, _ in p.bwd]
+        assert bn.count("coclr_conv_wgrad") + bn.count("coclr_conv_wgrad_s2d") == 53 + 2
+        assert bn.count("coclr_conv_igemm") == 52 + 2
+        assert bn.count("coclr_bn_bwd") == 53
+        res = [t for t in g.tensors if t.residual is not None]
+        assert len(res) == 16 and sum(1 for t in res if t.residual.name.endswith(".ds")) == 4
     finally:
         L.DRY_RUN = False
