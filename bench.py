@@ -24,7 +24,8 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 CFG = dict(network="s3d", dim=128, K=2048, m=0.999, T=0.07, B=32, seq_len=32, img=128)
-GFLOP_PER_PAIR = 91.46  # q fwd+dgrad+wgrad, k fwd (conv MACs x2), one clip pair
+GFLOP_PER_PAIR = {"s3d": 91.46, "r50": 231.67}  # q fwd+dgrad+wgrad, k fwd (conv MACs x2), one clip pair
+NET_NAME = {"s3d": "S3D", "r50": "R2D3D-50"}
 
 
 def parse():
@@ -34,6 +35,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="coclr_b200", choices=["coclr_b200", "reference"])
     ap.add_argument("--precision", default="parity", choices=["parity", "mixed", "fast"])
+    ap.add_argument("--net", default=CFG["network"], choices=["s3d", "r50"],
+                    help="backbone: s3d = BASELINE.json configs 1-4 (headline), r50 = config 5 (ResNet2d3d-50)")
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--seq_len", type=int, default=CFG["seq_len"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -93,11 +96,11 @@ def usable_cores():
     return env if env > 0 else n
 
 
-def cpu_oracle_clips_per_s(batch, seq_len, img, K, steps, warmup):
+def cpu_oracle_clips_per_s(batch, seq_len, img, K, steps, warmup, net="s3d"):
     from oracle import coclr_oracle as O
     torch.set_num_threads(usable_cores())
     torch.manual_seed(0)
-    sd = O.synth_state(O.infonce_shapes(128, K), seed=0)
+    sd = O.synth_state(O.infonce_shapes(128, K, network=net), seed=0)
     for k in O.param_keys(sd, "encoder_q."):
         sd[k].requires_grad_(True)
     state = {}
@@ -128,12 +131,12 @@ def reference_arm(args):
         return
     batch, sample_T = 1, 8
     steps = max(1, min(args.steps, 3))
-    val, med = cpu_oracle_clips_per_s(batch, sample_T, CFG["img"], CFG["K"], steps, 1)
-    line = {"impl": "reference", "metric": "clips/sec S3D InfoNCE (32x128^2, K=2048)", "value": val, "unit": "clips/s",
+    val, med = cpu_oracle_clips_per_s(batch, sample_T, CFG["img"], CFG["K"], steps, 1, args.net)
+    line = {"impl": "reference", "metric": "clips/sec %s InfoNCE (32x128^2, K=2048)" % NET_NAME[args.net], "value": val, "unit": "clips/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": med * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "InfoNCE S3D moco-k=2048 128^2 full train step (fwd+bwd+Adam), bounded sample: "
-                                   "%d clip pair(s) of %d frames per step, scaled to 32-frame clips" % (batch, sample_T),
+            "config": {"workload": "InfoNCE %s moco-k=2048 128^2 full train step (fwd+bwd+Adam), bounded sample: "
+                                   "%d clip pair(s) of %d frames per step, scaled to 32-frame clips" % (NET_NAME[args.net], batch, sample_T),
                        "batch_per_step": batch, "sample_seq_len": sample_T},
             "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": "oracle port of the reference (torch CPU fp32), %d timed steps of %d pair(s) of "
@@ -152,14 +155,16 @@ def conv_flops(cv):
         pix = cv.B * cv.src.T * cv.src.H * cv.src.W
         return 2.0 * pix * cv.N * cv.g.kt * cv.g.kh * cv.g.kw * cv.src.C
     pix = cv.B * cv.Td * cv.Hd * cv.Wd
-    if cv.src.C == 16 and cv.g.kh == 4 and cv.g.kw == 4:   # space-to-depth stem: the 7x7x3 conv it implements
-        return 2.0 * pix * cv.N * 147
+    if cv.src.C == 16 and cv.g.kh == 4 and cv.g.kw == 4:   # space-to-depth stem: the (kt,7,7)x3 conv it implements
+        return 2.0 * pix * cv.N * cv.g.kt * 147
     cin = 3 if cv.src.C == 8 else cv.src.C   # RGB input padded to 8 channels when the s2d stem is off
     return 2.0 * pix * cv.N * cv.g.kt * cv.g.kh * cv.g.kw * cin
 
 
 def wgrad_flops(wg):
     pix = wg.B * wg.Td * wg.Hd * wg.Wd
+    if wg.src.C == 16 and wg.g.kh == 4 and wg.g.kw == 4:   # space-to-depth stem: count the (kt,7,7)x3 conv it implements
+        return 2.0 * pix * wg.Cout * wg.g.kt * 147
     return 2.0 * pix * wg.Cout * wg.g.kt * wg.g.kh * wg.g.kw * wg.Cin_real
 
 
@@ -209,7 +214,7 @@ def main():
 
     B, T, HW, K = args.batch, args.seq_len, CFG["img"], CFG["K"]
     torch.manual_seed(0)                                   # main_nce.py:97-99
-    model = InfoNCE(CFG["network"], CFG["dim"], K, CFG["m"], CFG["T"], precision=args.precision).to(dev).train()
+    model = InfoNCE(args.net, CFG["dim"], K, CFG["m"], CFG["T"], precision=args.precision).to(dev).train()
     opt = moco.FlatAdam(model.encoder_q, lr=1e-3, weight_decay=1e-5)
     gen = torch.Generator().manual_seed(1000 + rank)
     host_blocks = [torch.randn(B, 2, 3, T, HW, HW, generator=gen).pin_memory() for _ in range(2)]
@@ -305,10 +310,20 @@ def main():
     cv = table.get("coclr_conv_igemm", {"ms": 0.0, "flops": 0.0, "launches": 0})
     wg = table.get("coclr_conv_wgrad", {"ms": 0.0, "flops": 0.0, "launches": 0})
     passes = 3 if args.precision == "parity" else None
+    # DRAM traffic of the heaviest coclr_conv_igemm launch of the step (Conv_2c.conv1 forward) from the committed
+    # `ncu --set full` capture; its algorithmic bytes are one read of the fp16 hi/lo input planes + one fp32 write
+    traffic, traffic_note = None, None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")))["ncu_r01_fwd_conv2c.ncu-rep"]
+        traffic = (cap["dram__bytes_read.sum"]["value"] + cap["dram__bytes_write.sum"]["value"]) * 1e6
+        traffic_note = ("bytes of ONE launch: Conv_2c.conv1 forward, M=524288 N=192 K=576 (profiles/r01_ncu_full_summary.json); "
+                        "algorithmic = 134.2e6 (input planes, read once) + 402.7e6 (fp32 output) bytes")
+    except Exception:
+        pass
     achieved = cv["flops"] / (cv["ms"] * 1e-3) / 1e12 if cv["ms"] > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "coclr_conv_igemm (forward + dgrad implicit GEMM)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic if args.net == "s3d" else None, "traffic_note": traffic_note, "peak_source": peak_src,
                 "launches_per_step": cv["launches"], "ms_per_step_in_kernel": cv["ms"],
                 "mode": "%s (forward %s, backward %s)" % (args.precision,
                                                         "3 MMA passes fp16 hi/lo" if args.precision != "fast" else "1 pass bf16",
@@ -347,26 +362,26 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             try:
-                v, med = cpu_oracle_clips_per_s(1, 8, HW, K, 2, 1)
+                v, med = cpu_oracle_clips_per_s(1, 8, HW, K, 2, 1, args.net)
                 cpu = {"value": v, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
                        "sample": "oracle port (torch CPU fp32) full train step on 1 pair of 8-frame 128^2 clips "
                                  "(= 0.5 clip of 32 frames), 2 timed steps after 1 warm-up, %.1f s/step" % med}
             except Exception as ex:  # pragma: no cover
                 cpu = {"value": None, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
                        "sample": "failed: %r" % (ex,)}
-        line = {"metric": "clips/sec S3D InfoNCE (32x128^2, K=2048)", "value": value, "unit": "clips/s",
+        line = {"metric": "clips/sec %s InfoNCE (32x128^2, K=2048)" % NET_NAME[args.net], "value": value, "unit": "clips/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (fp16/bf16 hi-lo split operands, fp32 accumulate)" if args.precision == "parity" else
                          ("bf16" if args.precision == "fast" else "f32 forward / bf16 backward"),
                 "data": "synthetic",
-                "config": {"workload": "InfoNCE S3D moco-k=2048 bs=%d/GPU seq_len=%d 128^2, full train step "
+                "config": {"workload": "InfoNCE %s moco-k=2048 bs=%d/GPU seq_len=%d 128^2, full train step "
                                        "(q fwd, EMA, shuffle-BN k fwd, fused logits+CE, enqueue, bwd, all-reduce, Adam)"
-                                       % (B, T),
+                                       % (NET_NAME[args.net], B, T),
                            "global_batch": B * world, "parallelism": "dp%d" % world, "precision": args.precision,
                            "l2": "two alternating 403 MB input blocks per rank (> 126 MB L2)",
                            "pairs_per_s": value / 2, "final_loss": final_loss, "host_enqueue_ms_per_step": host_ms,
-                           "algorithmic_tflops": value / 2 * GFLOP_PER_PAIR / 1e3},
+                           "algorithmic_tflops": value / 2 * GFLOP_PER_PAIR[args.net] * (T / 32.0) / 1e3},
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline}
         if cpu is not None:
