@@ -216,7 +216,7 @@ def main_worker(args):
         missing = model.load_state_dict(ckpt['state_dict'], strict=not args.pretrain)
         print('loaded %s (epoch %s) %s' % (path, ckpt.get('epoch'), missing if args.pretrain else ''))
         if args.resume:
-            args.start_epoch = ckpt['epoch']
+            args.start_epoch = ckpt['epoch'] + 1              # reference main_nce.py:218
             args.iteration = ckpt.get('iteration', 1)
             best_acc = ckpt.get('best_acc', 0.0)
             if not args.reset_lr and isinstance(ckpt.get('optimizer'), dict) and 'exp_avg' in ckpt['optimizer']:
