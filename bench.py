@@ -143,7 +143,7 @@ def reference_arm(args):
                                        "%d-frame 128^2 clips after 1 warm-up, counted as %d/32 clips each; the reference "
                                        "is pure Python and cannot travel to the GPU box" % (steps, batch, sample_T, sample_T)},
             "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -193,8 +193,32 @@ def kernel_breakdown(run_step):
     return table, prof
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, ...) write to fd 1; the contract is ONE JSON line on stdout. Point fd 1 at
+    stderr for the run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         reference_arm(args)
         return
@@ -386,7 +410,7 @@ def main():
                 "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
