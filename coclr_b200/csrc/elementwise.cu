@@ -687,12 +687,13 @@ __global__ void avgpool_bwd_kernel(const float* dfeat, float* dA, int ld, int co
 __global__ void __launch_bounds__(256) pack_input_kernel(const float* x, long batch_stride, long chan_stride, int Cin,
                                                          uint16_t* out_hi, uint16_t* out_lo, uint16_t* out2_hi,
                                                          uint16_t* out2_lo, int B, long thw,
-                                                         const long* __restrict__ batch_index) {
+                                                         const long* __restrict__ batch_index,
+                                                         const float* const* __restrict__ peer_x, int cpp) {
   const long total = (long)B * thw;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long b = i / thw, p = i - b * thw;
     const long sb = batch_index ? batch_index[b] : b;  // shuffle-BN gather folded in (pretrain.py:124)
-    const float* s = x + sb * batch_stride + p;
+    const float* s = (peer_x ? peer_x[sb / cpp] + (sb % cpp) * batch_stride : x + sb * batch_stride) + p;
     uint16_t h[8], l[8];
     float vv[8];
 #pragma unroll
@@ -720,7 +721,8 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* x, long ba
 __global__ void __launch_bounds__(256) pack_input_s2d_kernel(const float* x, long batch_stride, long chan_stride,
                                                              int Cin, uint16_t* out_hi, uint16_t* out_lo,
                                                              uint16_t* out2_hi, uint16_t* out2_lo, int B, int T, int H,
-                                                             int W, const long* __restrict__ batch_index) {
+                                                             int W, const long* __restrict__ batch_index,
+                                                             const float* const* __restrict__ peer_x, int cpp) {
   const int H2 = H >> 1, W2 = W >> 1;
   const long total = (long)B * T * H2 * W2;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -730,7 +732,8 @@ __global__ void __launch_bounds__(256) pack_input_s2d_kernel(const float* x, lon
     const int t = (int)(r % T);
     const long b = r / T;
     const long sb = batch_index ? batch_index[b] : b;
-    const float* s = x + sb * batch_stride + ((long)t * H + 2 * Y) * W + 2 * X;
+    const float* base = peer_x ? peer_x[sb / cpp] + (sb % cpp) * batch_stride : x + sb * batch_stride;
+    const float* s = base + ((long)t * H + 2 * Y) * W + 2 * X;
     float vv[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) vv[j] = 0.f;
@@ -974,22 +977,27 @@ extern "C" int coclr_avgpool_bwd(const float* dfeat, float* dA, int ld, int coff
 
 extern "C" int coclr_pack_input(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi, void* out_lo,
                                 void* out2_hi, void* out2_lo, int B, long thw, const long* batch_index,
-                                coclr_stream_t stream) {
-  if (!x || !out_hi || Cin < 1 || Cin > 8) return COCLR_E_ARG;
+                                const void* const* peer_x, int clips_per_peer, coclr_stream_t stream) {
+  if ((!x && !peer_x) || !out_hi || Cin < 1 || Cin > 8) return COCLR_E_ARG;
+  if (peer_x && (!batch_index || clips_per_peer < 1)) return COCLR_E_ARG;
   pack_input_kernel<<<grid_for((long)B * thw, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
       x, batch_stride, chan_stride, Cin, reinterpret_cast<uint16_t*>(out_hi), reinterpret_cast<uint16_t*>(out_lo),
-      reinterpret_cast<uint16_t*>(out2_hi), reinterpret_cast<uint16_t*>(out2_lo), B, thw, batch_index);
+      reinterpret_cast<uint16_t*>(out2_hi), reinterpret_cast<uint16_t*>(out2_lo), B, thw, batch_index,
+      reinterpret_cast<const float* const*>(peer_x), clips_per_peer);
   return LAUNCH_OK();
 }
 
 extern "C" int coclr_pack_input_s2d(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi,
                                     void* out_lo, void* out2_hi, void* out2_lo, int B, int T, int H, int W,
-                                    const long* batch_index, coclr_stream_t stream) {
-  if (!x || !out_hi || Cin < 1 || Cin > 4 || (H & 1) || (W & 1)) return COCLR_E_ARG;
+                                    const long* batch_index, const void* const* peer_x, int clips_per_peer,
+                                    coclr_stream_t stream) {
+  if ((!x && !peer_x) || !out_hi || Cin < 1 || Cin > 4 || (H & 1) || (W & 1)) return COCLR_E_ARG;
+  if (peer_x && (!batch_index || clips_per_peer < 1)) return COCLR_E_ARG;
   const long total = (long)B * T * (H / 2) * (W / 2);
   pack_input_s2d_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
       x, batch_stride, chan_stride, Cin, reinterpret_cast<uint16_t*>(out_hi), reinterpret_cast<uint16_t*>(out_lo),
-      reinterpret_cast<uint16_t*>(out2_hi), reinterpret_cast<uint16_t*>(out2_lo), B, T, H, W, batch_index);
+      reinterpret_cast<uint16_t*>(out2_hi), reinterpret_cast<uint16_t*>(out2_lo), B, T, H, W, batch_index,
+      reinterpret_cast<const float* const*>(peer_x), clips_per_peer);
   return LAUNCH_OK();
 }
 

@@ -762,10 +762,12 @@ class EncoderEngine:
             main.wait_stream(side)
         L.LAUNCHES += sum(L.KERNELS_PER_CALL.get(fn.__name__, 1) for fn, _ in oplist)
 
-    def forward(self, x, training=True, with_backward=False, repack=True, batch_index=None, batch=None):
+    def forward(self, x, training=True, with_backward=False, repack=True, batch_index=None, batch=None, peers=None):
         """x: [*, C, T, H, W] fp32 CUDA (any batch stride). Clip b of the pass is x[batch_index[b]] when a
-        device int64 index is given (shuffle-BN gather), else x[b].  Returns the plan; plan.q holds the
-        normalised features [B, dim] (plan.backbone_out the backbone output when there is no head)."""
+        device int64 index is given (shuffle-BN gather), else x[b].  peers = (device pointer of an array with one
+        peer-mapped clip buffer per rank, clips per rank): batch_index then is a GLOBAL clip index and the clips are
+        read straight from the owning ranks' buffers (same layout as x) over NVLink.  Returns the plan; plan.q holds
+        the normalised features [B, dim] (plan.backbone_out the backbone output when there is no head)."""
         if not x.is_cuda:
             raise L.CoclrError("coclr_b200 encoders run on CUDA only (no CPU fallback)")
         _, Cin, T, H, W = x.shape
@@ -777,18 +779,20 @@ class EncoderEngine:
         p = self.plan(B, T, H, W, training, with_backward)
         lib = L.load()
         tw = p.input.plw if (p.input.plw is not None and p.input.plw is not p.input.pl) else None
+        peer_ptr, cpp = (C.c_void_p(int(peers[0])), int(peers[1])) if peers is not None else (None, 0)
+        assert peers is None or batch_index is not None
         # the clip pointer / shuffle index change from call to call, so packing stays outside the captured graph
         if self.graph.stem_s2d:
             assert H % 2 == 0 and W % 2 == 0, "the space-to-depth stem needs even H, W"
             L.check(lib.coclr_pack_input_s2d(L.dptr(x), x.stride(0), x.stride(1), Cin, L.dptr(p.input.pl.hi),
                                              L.dptr(p.input.pl.lo), L.dptr(tw.hi) if tw else None,
                                              L.dptr(tw.lo) if tw else None, B, T, H, W, L.dptr(batch_index),
-                                             L.stream_ptr()), "coclr_pack_input_s2d")
+                                             peer_ptr, cpp, L.stream_ptr()), "coclr_pack_input_s2d")
         else:
             L.check(lib.coclr_pack_input(L.dptr(x), x.stride(0), x.stride(1), Cin, L.dptr(p.input.pl.hi),
                                          L.dptr(p.input.pl.lo), L.dptr(tw.hi) if tw else None,
                                          L.dptr(tw.lo) if tw else None, B, T * H * W, L.dptr(batch_index),
-                                         L.stream_ptr()), "coclr_pack_input")
+                                         peer_ptr, cpp, L.stream_ptr()), "coclr_pack_input")
 
         def body():
             if repack:

@@ -36,6 +36,29 @@ def concat_all_gather(tensor):
     return out
 
 
+class PeerClips:
+    """Key clips of every rank, readable from every rank: two symmetric-memory staging buffers (NVLink peer-mapped via
+    torch.distributed._symmetric_memory) per rank.  publish() copies the local clips in and runs a device-side
+    barrier on the current stream; afterwards any rank may read any rank's clips with plain loads (the packing
+    kernel does, coclr_pack_input*), so the all-gather of all clips (model/pretrain.py:105-106: W x 201 MB received
+    per rank) shrinks to P2P reads of the B clips a rank actually encodes.  Double buffering makes the next
+    publish() safe without a second barrier: a rank overwrites buffer i two steps later, after the barrier of the
+    step in between, which every peer only passes once its reads of buffer i have been queued before it."""
+
+    def __init__(self, shape, device, group):
+        import torch.distributed._symmetric_memory as symm
+        self.bufs = [symm.empty(*shape, dtype=torch.float32, device=device) for _ in range(2)]
+        self.hdls = [symm.rendezvous(b, group) for b in self.bufs]
+        self.cur = 0
+
+    def publish(self, x):
+        buf, hdl = self.bufs[self.cur], self.hdls[self.cur]
+        self.cur ^= 1
+        buf.copy_(x)
+        hdl.barrier()
+        return buf, hdl.buffer_ptrs_dev
+
+
 class _EncodeFn(torch.autograd.Function):
     """Encoder pass as one autograd node; the parameter gradients are written straight into the
     encoder's flat gradient buffer (the nn.Parameter .grad fields are views of it)."""
@@ -96,7 +119,7 @@ class MoCoEncoder(nn.Sequential):
             st.grad.zero_()
             st.attach_grads(dict(self.named_parameters()))
 
-    def encode(self, x, batch_index=None, batch=None):
+    def encode(self, x, batch_index=None, batch=None, peers=None):
         """L2-normalised features [B, dim] of clips x[B,C,T,H,W] (what the reference obtains with
         F.normalize(encoder(x), dim=1).view(B, dim); model/pretrain.py:153-155,165-167)."""
         eng = self._engine_for(x.device)
@@ -104,7 +127,8 @@ class MoCoEncoder(nn.Sequential):
         if want_grad:
             assert batch_index is None
             return _EncodeFn.apply(self._anchor, self, x, self.training)
-        plan = eng.forward(x, training=self.training, with_backward=False, batch_index=batch_index, batch=batch)
+        plan = eng.forward(x, training=self.training, with_backward=False, batch_index=batch_index, batch=batch,
+                           peers=peers)
         return plan.q.clone()
 
     def forward(self, x):

@@ -14,6 +14,8 @@ What changed under the surface:
   * logits + temperature + cross-entropy by-products come from one kernel (:175-182);
   * queue_ptr is mirrored on the host, so there is no `int(self.queue_ptr)` device sync per step (:89).
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -49,6 +51,7 @@ class InfoNCE(nn.Module):
         self.register_buffer("queue_ptr", torch.zeros(1, dtype=torch.long))
         self._ptr_host = None
         self._side_stream = None
+        self._peer_clips = {}     # clip shape -> moco.PeerClips, or False when symmetric memory is unavailable
 
     # -- queue pointer mirror ---------------------------------------------------------------------
     def _load_from_state_dict(self, *args, **kwargs):
@@ -76,16 +79,43 @@ class InfoNCE(nn.Module):
         encoder = self.encoder_k if encoder is None else encoder
         world, rank = moco._world()
         B = x2.shape[0]
-        x_gather = concat_all_gather(x2) if world > 1 else x2
+        peer = self._peer_exchange(x2) if world > 1 else None
+        if peer is None:
+            x_gather = concat_all_gather(x2) if world > 1 else x2                     # :105-106
+        else:
+            x_gather, peer_ptrs = peer.publish(x2)      # own clips; the other ranks' are read in place over NVLink
         idx_shuffle = torch.randperm(B * world).to(x2.device, non_blocking=True)     # CPU RNG draw, as :112
         if world > 1:
             dist.broadcast(idx_shuffle, src=0)                                       # :115
         idx_unshuffle = torch.argsort(idx_shuffle)
         idx_this = idx_shuffle.view(world, -1)[rank].contiguous()
-        k_sh = encoder.encode(x_gather, batch_index=idx_this, batch=B)            # x_gather[idx_this], :124
+        k_sh = encoder.encode(x_gather, batch_index=idx_this, batch=B,            # x_gather[idx_this], :124
+                              peers=(peer_ptrs, B) if peer is not None else None)
         k_all = concat_all_gather(k_sh) if world > 1 else k_sh
         k_global = k_all[idx_unshuffle].contiguous()                                  # :143 for every rank
         return k_global[rank * B:(rank + 1) * B], k_global
+
+    peer_shuffle = os.environ.get("COCLR_PEER_SHUFFLE", "1") != "0"
+
+    def _peer_exchange(self, x2):
+        """PeerClips for this clip shape, or None (-> all-gather path) when peer memory cannot be set up (no NVLink /
+        P2P between the ranks, non-NCCL backend) or is switched off with COCLR_PEER_SHUFFLE=0."""
+        if not InfoNCE.peer_shuffle or not x2.is_cuda or dist.get_backend() != "nccl":
+            return None
+        key = tuple(x2.shape)
+        pc = self._peer_clips.get(key)
+        if pc is None:
+            ok = torch.ones(1, device=x2.device)
+            try:
+                pc = moco.PeerClips(key, x2.device, dist.group.WORLD)
+            except Exception as ex:  # pragma: no cover - depends on the machine
+                print("coclr_b200: peer-memory key exchange unavailable (%r); using all-gather" % (ex,))
+                pc, ok[0] = False, 0
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)       # all ranks take the same path
+            if float(ok) < 1:
+                pc = False
+            self._peer_clips[key] = pc
+        return pc or None
 
     @torch.no_grad()
     def _dequeue_and_enqueue(self, keys_global):

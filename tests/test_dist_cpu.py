@@ -30,7 +30,7 @@ def _worker(rank, world, port, out):
     torch.manual_seed(0)
     B, K = 4, 32
     m = InfoNCE("s3d", 128, K)
-    m.encoder_k.encode = lambda x, batch_index=None, batch=None: _fake_encode(x[batch_index] if batch_index is not None else x)
+    m.encoder_k.encode = lambda x, batch_index=None, batch=None, peers=None: _fake_encode(x[batch_index] if batch_index is not None else x)
     moco.enqueue = lambda queue, keys, ptr: queue.__setitem__((slice(None), slice(ptr, ptr + keys.shape[0])), keys.T)
     g = torch.Generator().manual_seed(100 + rank)
     x2 = torch.randn(B, 3, 2, 8, 8, generator=g)
