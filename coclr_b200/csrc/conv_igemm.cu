@@ -106,10 +106,14 @@ template <bool kLo, int NI>
 COCLR_DEVINL void gather_block_async(const coclr_src_t& S, const coclr_geom_t& G, int Kreal, const TapPos& tp, int ck,
                                      int r0, const int* rb, const int* rt, const int* ry, const int* rx,
                                      uint32_t blk_hi, uint32_t blk_lo) {
+  // This runs once per (row, K chunk) in warps that share their issue slots with everything else on the SM: for
+  // narrow layers (N <= 64) the MMAs of a chunk take ~600 cycles, so the address arithmetic is kept to 32-bit pixel
+  // indices (host side guarantees B*T*H*W < 2^31) and one widening multiply per row.
   const bool kvalid = tp.k0 < Kreal;
-  const int ta = tp.ta, ya = tp.ya, xa = tp.xa, ci = tp.ci;
-  const uint16_t* hi = reinterpret_cast<const uint16_t*>(S.hi);
-  const uint16_t* lo = reinterpret_cast<const uint16_t*>(S.lo);
+  const int ta = tp.ta, ya = tp.ya, xa = tp.xa;
+  const uint16_t* hi = reinterpret_cast<const uint16_t*>(S.hi) + (S.coff + tp.ci);
+  const uint16_t* lo = reinterpret_cast<const uint16_t*>(S.lo) + (S.coff + tp.ci);
+  const int HW = S.H * S.W;
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
     bool in = kvalid && rb[i] >= 0;
@@ -122,14 +126,13 @@ COCLR_DEVINL void gather_block_async(const coclr_src_t& S, const coclr_geom_t& G
       ts = rt[i] - ta;
       ys = ry[i] - ya;
       xs = rx[i] - xa;
-      in = in && (ts >= 0) && (ys >= 0) && (xs >= 0);
-      if (G.st == 2) { in = in && !(ts & 1); ts >>= 1; }
+      if (G.st == 2) { in = in && !(ts & 1); ts >>= 1; }   // arithmetic shifts keep negatives negative
       if (G.sh == 2) { in = in && !(ys & 1); ys >>= 1; }
       if (G.sw == 2) { in = in && !(xs & 1); xs >>= 1; }
     }
     in = in && ((unsigned)ts < (unsigned)S.T) && ((unsigned)ys < (unsigned)S.H) && ((unsigned)xs < (unsigned)S.W);
-    size_t off = 0;
-    if (in) off = ((((size_t)rb[i] * S.T + ts) * S.H + ys) * S.W + xs) * (size_t)S.ld + S.coff + ci;
+    const int pix = in ? (rb[i] * S.T + ts) * HW + ys * S.W + xs : 0;
+    const size_t off = (size_t)(unsigned)pix * (unsigned)S.ld;
     const uint32_t dst = swz128_offset((uint32_t)(r0 + 32 * i), (uint32_t)ck);
     const uint32_t nbytes = in ? 16u : 0u;
     cp_async16(blk_hi + dst, hi + off, nbytes);
@@ -175,6 +178,25 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(int BN, int n_tiles, 
   L.off_bars = (L.off_stats + stat_bytes + 15u) & ~15u;
   L.total = L.off_bars + 256u + 1024u;
   return L;
+}
+
+// Transposed (dgrad) pass of a temporally strided conv: a tap only meets every other output frame, so for a tile that
+// lies inside ONE frame (Hd*Wd % 128 == 0) and K chunks that lie inside one tap (C % 64 == 0) whole chunks are zero.
+// Bit kc of the returned mask = chunk kc contributes nothing to this tile; producers, weight loader and MMA issuer all
+// derive the same mask and skip those chunks.  0 when the shortcut does not apply.
+COCLR_DEVINL uint64_t zero_chunk_mask(const coclr_conv_t& P, int nkc, int m_tile) {
+  if (!P.g.transposed || P.g.st != 2 || (P.src.C & 63) || ((P.Hd * P.Wd) % kTileM) || nkc > 64) return 0ull;
+  const int tt = ((m_tile * kTileM) / (P.Hd * P.Wd)) % P.Td + P.g.pt;
+  const int chunks_per_plane = (P.src.C >> 6) * P.g.kh * P.g.kw;   // K chunks that share one temporal tap
+  uint64_t mask = 0ull;
+  int ta = 0, left = chunks_per_plane;
+  for (int kc = 0; kc < nkc; ++kc) {
+    const int ts = tt - ta;
+    if (ts < 0 || (ts & 1) || (ts >> 1) >= P.src.T) mask |= 1ull << kc;
+    if (--left == 0) { left = chunks_per_plane; ++ta; }
+  }
+  if (mask == (nkc >= 64 ? ~0ull : ((1ull << nkc) - 1ull))) mask &= ~1ull;  // keep one chunk: it zero-fills the accumulator
+  return mask;
 }
 
 template <int kNPass>
@@ -239,7 +261,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
       for (int i = 0; i < 4; ++i)
         row_coords(P.g, P.Td, P.Hd, P.Wd, M, m_tile * kTileM + r0 + 32 * i, rb[i], rt[i], ry[i], rx[i]);
       TapPos tp = tap0;
+      const uint64_t zmask = zero_chunk_mask(P, nkc, m_tile);
       for (int kc = 0; kc < nkc; ++kc) {
+        if ((zmask >> kc) & 1ull) {
+          tap_advance(tp, P.src, P.g, kChunkK);
+          continue;
+        }
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         const uint32_t sa = smem_base + stage * L.stage_bytes;
         gather_block_async<kLo, 4>(P.src, P.g, P.Kreal, tp, ck, r0, rb, rt, ry, rx, sa, sa + L.a_bytes);
@@ -257,7 +284,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % P.n_tiles;
+        const uint64_t zmask = zero_chunk_mask(P, nkc, tile / P.n_tiles);
         for (int kc = 0; kc < nkc; ++kc) {
+          if ((zmask >> kc) & 1ull) continue;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sb = smem + stage * L.stage_bytes + copies * L.a_bytes;
           const uint8_t* src =
@@ -276,11 +305,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1u;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      mbar_wait_spin(&tempty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * 256u;
+      const uint64_t zmask = zero_chunk_mask(P, nkc, tile / P.n_tiles);
+      uint32_t started = 0;   // 0 until the first MMA of the tile has overwritten the accumulator
       for (int kc = 0; kc < nkc; ++kc) {
-        mbar_wait(&full_bar[stage], phase);
+        if ((zmask >> kc) & 1ull) continue;
+        mbar_wait_spin(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * L.stage_bytes);
@@ -291,21 +323,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
             const uint64_t a_lo = make_smem_desc(sa + L.a_bytes, 16, 1024);
             const uint64_t b_lo = make_smem_desc(sb + L.b_bytes, 16, 1024);
 #pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, (kc | k) != 0);
+            for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, (started | k) != 0);
 #pragma unroll
             for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
 #pragma unroll
             for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
           } else {
 #pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (kc | k) != 0);
+            for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (started | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
-          if (kc == nkc - 1) umma_commit(&tfull_bar[acc]);
         }
+        started = 1u;
         __syncwarp();
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
+      if (lane == 0) umma_commit(&tfull_bar[acc]);   // fires when every MMA of this tile has completed
+      __syncwarp();
     }
   } else if (warp < kEpiWarps) {
     // ===================== epilogue =====================
@@ -576,7 +610,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
     const uint32_t idesc = make_idesc(P.dy_bf16 ? 1u : 0u, P.src_bf16 ? 1u : 0u, 1u, 1u, 128u, (uint32_t)BNk);
     uint32_t stage = 0, phase = 0;
     for (int ch = 0; ch < nch; ++ch) {
-      mbar_wait(&full_bar[stage], phase);
+      mbar_wait_spin(&full_bar[stage], phase);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t s_dy = smem_u32(smem + stage * L.stage_bytes);
@@ -732,6 +766,7 @@ extern "C" int coclr_pack_weights(const coclr_pack_t* p, coclr_stream_t stream) 
 
 static bool src_ok(const coclr_src_t& s, int need_lo) {
   if (!s.hi || (need_lo && !s.lo)) return false;
+  if (s.T < 1 || s.H < 1 || s.W < 1) return false;
   if (s.C % 8 != 0 || s.ld % 8 != 0 || s.coff % 8 != 0) return false;  // 16-byte cp.async granules
   if (((uintptr_t)s.hi & 15) || ((uintptr_t)s.lo & 15)) return false;
   return true;
@@ -760,6 +795,7 @@ extern "C" int coclr_conv_igemm(const coclr_conv_t* p, int num_sms, coclr_stream
   if ((p->g.st != 1 && p->g.st != 2) || (p->g.sh != 1 && p->g.sh != 2) || (p->g.sw != 1 && p->g.sw != 2))
     return COCLR_E_ARG;
   if (num_sms <= 0) return COCLR_E_ARG;
+  if ((long long)p->B * p->src.T * p->src.H * p->src.W >= (1ll << 31)) return COCLR_E_ARG;  // 32-bit pixel indices
   cudaStream_t s = (cudaStream_t)stream;
   return p->npass > 1 ? launch_conv<3>(*p, num_sms, s) : launch_conv<1>(*p, num_sms, s);
 }
@@ -784,6 +820,9 @@ extern "C" int coclr_conv_wgrad(const coclr_wgrad_t* p, coclr_stream_t stream) {
   if (!p || !p->dw) return COCLR_E_ARG;
   if (!src_ok(p->src, p->npass > 1) || !src_ok(p->dy, p->npass > 1)) return COCLR_E_ARG;
   if (p->splits < 1 || p->g.transposed) return COCLR_E_ARG;
+  if ((long long)p->B * p->src.T * p->src.H * p->src.W >= (1ll << 31) ||
+      (long long)p->B * p->dy.T * p->dy.H * p->dy.W >= (1ll << 31))
+    return COCLR_E_ARG;  // 32-bit pixel indices
   cudaStream_t s = (cudaStream_t)stream;
   return p->npass > 1 ? launch_wgrad<3>(*p, s) : launch_wgrad<1>(*p, s);
 }

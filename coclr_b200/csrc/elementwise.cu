@@ -718,8 +718,9 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* x, long ba
 // Space-to-depth variant for the stride-2 7x7 stem (backbone/s3dg.py:145): out[b, t, Y, X, (dy*2+dx)*Cin + c] =
 // x[b, c, t, 2Y+dy, 2X+dx], 16 channels per pixel (4*Cin = 12 real + zeros).  The stem then is a stride-1
 // 4x4 convolution over 16-channel pixels: 32-byte gather granules and 16 instead of 49 taps.
+template <int Cin>
 __global__ void __launch_bounds__(256) pack_input_s2d_kernel(const float* x, long batch_stride, long chan_stride,
-                                                             int Cin, uint16_t* out_hi, uint16_t* out_lo,
+                                                             uint16_t* out_hi, uint16_t* out_lo,
                                                              uint16_t* out2_hi, uint16_t* out2_lo, int B, int T, int H,
                                                              int W, const long* __restrict__ batch_index,
                                                              const float* const* __restrict__ peer_x, int cpp) {
@@ -737,16 +738,41 @@ __global__ void __launch_bounds__(256) pack_input_s2d_kernel(const float* x, lon
     float vv[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) vv[j] = 0.f;
+    // (dx = 0, 1) are adjacent floats at an even offset: one 8-byte load per (channel, dy)
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx)
-        for (int c = 0; c < Cin; ++c) vv[(dy * 2 + dx) * Cin + c] = s[(long)c * chan_stride + dy * W + dx];
+      for (int c = 0; c < Cin; ++c) {
+        const float2 p2 = *reinterpret_cast<const float2*>(s + (long)c * chan_stride + dy * W);
+        vv[(dy * 2 + 0) * Cin + c] = p2.x;
+        vv[(dy * 2 + 1) * Cin + c] = p2.y;
+      }
+    uint32_t hw[8], lw[8], h2[8], l2[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 v4 = make_float4(vv[4 * q], vv[4 * q + 1], vv[4 * q + 2], vv[4 * q + 3]);
-      st_pair4<false>(out_hi, out_lo, (size_t)i * 16 + 4 * q, v4);
-      if (out2_hi != nullptr) st_pair4<true>(out2_hi, out2_lo, (size_t)i * 16 + 4 * q, v4);
+    for (int j = 0; j < 8; ++j) {
+      uint16_t a, b, c2, d;
+      split2<false>(vv[2 * j], a, b);
+      split2<false>(vv[2 * j + 1], c2, d);
+      hw[j] = (uint32_t)a | ((uint32_t)c2 << 16);
+      lw[j] = (uint32_t)b | ((uint32_t)d << 16);
+      if (out2_hi != nullptr) {
+        split2<true>(vv[2 * j], a, b);
+        split2<true>(vv[2 * j + 1], c2, d);
+        h2[j] = (uint32_t)a | ((uint32_t)c2 << 16);
+        l2[j] = (uint32_t)b | ((uint32_t)d << 16);
+      }
+    }
+    const size_t o = (size_t)i * 16;
+    auto st32 = [](uint16_t* p, size_t off, const uint32_t* w) {
+      uint4* q = reinterpret_cast<uint4*>(p + off);
+      q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    };
+    st32(out_hi, o, hw);
+    if (out_lo != nullptr) st32(out_lo, o, lw);
+    if (out2_hi != nullptr) {
+      st32(out2_hi, o, h2);
+      if (out2_lo != nullptr) st32(out2_lo, o, l2);
     }
   }
 }
@@ -994,10 +1020,19 @@ extern "C" int coclr_pack_input_s2d(const float* x, long batch_stride, long chan
   if ((!x && !peer_x) || !out_hi || Cin < 1 || Cin > 4 || (H & 1) || (W & 1)) return COCLR_E_ARG;
   if (peer_x && (!batch_index || clips_per_peer < 1)) return COCLR_E_ARG;
   const long total = (long)B * T * (H / 2) * (W / 2);
-  pack_input_s2d_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
-      x, batch_stride, chan_stride, Cin, reinterpret_cast<uint16_t*>(out_hi), reinterpret_cast<uint16_t*>(out_lo),
-      reinterpret_cast<uint16_t*>(out2_hi), reinterpret_cast<uint16_t*>(out2_lo), B, T, H, W, batch_index,
-      reinterpret_cast<const float* const*>(peer_x), clips_per_peer);
+  if ((batch_stride | chan_stride) & 1) return COCLR_E_ARG;  // 8-byte loads of (x, x+1) pairs
+#define COCLR_PACK_S2D(CIN)                                                                                         \
+  pack_input_s2d_kernel<CIN><<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(                    \
+      x, batch_stride, chan_stride, reinterpret_cast<uint16_t*>(out_hi), reinterpret_cast<uint16_t*>(out_lo),       \
+      reinterpret_cast<uint16_t*>(out2_hi), reinterpret_cast<uint16_t*>(out2_lo), B, T, H, W, batch_index,          \
+      reinterpret_cast<const float* const*>(peer_x), clips_per_peer)
+  switch (Cin) {
+    case 1: COCLR_PACK_S2D(1); break;
+    case 2: COCLR_PACK_S2D(2); break;
+    case 3: COCLR_PACK_S2D(3); break;
+    default: COCLR_PACK_S2D(4); break;
+  }
+#undef COCLR_PACK_S2D
   return LAUNCH_OK();
 }
 

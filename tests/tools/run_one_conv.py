@@ -12,7 +12,9 @@ mode = sys.argv[1]
 Cin, Cout, kt, kh, kw, B, T, H, W = [int(v) for v in sys.argv[2:11]]
 npass = int(sys.argv[11]) if len(sys.argv) > 11 else 3
 iters = int(sys.argv[12]) if len(sys.argv) > 12 else 5
-geom = ops.Geometry((kt, kh, kw), (1, 1, 1), (kt // 2, kh // 2, kw // 2))
+stride = tuple(int(v) for v in os.environ.get("STRIDE", "1,1,1").split(","))   # (B,T,H,W) are the conv INPUT dims
+geom = ops.Geometry((kt, kh, kw), stride, (kt // 2, kh // 2, kw // 2))
+To, Ho, Wo = geom.out_dims(T, H, W)
 dev = "cuda"
 r8 = lambda c: (c + 7) // 8 * 8
 w = torch.randn(Cout, Cin, kt, kh, kw, device=dev) * 0.05
@@ -20,15 +22,15 @@ if mode == "fwd":
     x = ops.Planes((B, T, H, W, r8(Cin)), 0, dev)
     x.hi.normal_(); x.lo.normal_(0, 1e-3)
     pw = ops.PackedWeights(Cout, Cin, geom.taps, r8(Cin), 0, 0, dev).pack(w)
-    dst = torch.empty(B, T, H, W, Cout, device=dev)
+    dst = torch.empty(B, To, Ho, Wo, Cout, device=dev)
     stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
-    run = lambda: ops.conv_igemm(x.src(0, r8(Cin), T, H, W), 0, geom.c(0), B, (T, H, W), pw, dst, stats=stats, npass=npass)
+    run = lambda: ops.conv_igemm(x.src(0, r8(Cin), T, H, W), 0, geom.c(0), B, (To, Ho, Wo), pw, dst, stats=stats, npass=npass)
 elif mode == "dgrad":
-    dy = ops.Planes((B, T, H, W, r8(Cout)), 1, dev)
+    dy = ops.Planes((B, To, Ho, Wo, r8(Cout)), 1, dev)
     dy.hi.normal_(); dy.lo.normal_(0, 1e-3)
     pw = ops.PackedWeights(Cout, Cin, geom.taps, r8(Cout), 1, 1, dev).pack(w)
     dst = torch.zeros(B, T, H, W, Cin, device=dev)
-    run = lambda: ops.conv_igemm(dy.src(0, r8(Cout), T, H, W), 1, geom.c(1), B, (T, H, W), pw, dst, accumulate=False, npass=npass)
+    run = lambda: ops.conv_igemm(dy.src(0, r8(Cout), To, Ho, Wo), 1, geom.c(1), B, (T, H, W), pw, dst, accumulate=False, npass=npass)
 else:
     x = ops.Planes((B, T, H, W, r8(Cin)), 1, dev)
     x.hi.normal_(); x.lo.normal_(0, 1e-3)
