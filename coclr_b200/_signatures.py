@@ -21,8 +21,8 @@ EXPORTS = {
     "coclr_maxpool_bwd": (I, [P, P]),
     "coclr_avgpool_fwd": (I, [P, P, I, I, I, P, I, I, I, P]),
     "coclr_avgpool_bwd": (I, [P, P, I, I, I, I, I, P]),
-    "coclr_pack_input": (I, [P, LG, LG, I, P, P, P, P, I, LG, P, P, I, P]),
-    "coclr_pack_input_s2d": (I, [P, LG, LG, I, P, P, P, P, I, I, I, I, P, P, I, P]),
+    "coclr_pack_input": (I, [P, LG, LG, I, P, P, P, P, I, LG, P, P, I, P, P, P]),
+    "coclr_pack_input_s2d": (I, [P, LG, LG, I, P, P, P, P, I, I, I, I, P, P, I, P, P, P]),
     "coclr_l2norm_fwd": (I, [P, P, P, P, I, I, P]),
     "coclr_l2norm_bwd": (I, [P, P, P, P, P, I, I, P]),
     "coclr_ema_update": (I, [P, P, F, F, LG, I, P]),

@@ -688,7 +688,9 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* x, long ba
                                                          uint16_t* out_hi, uint16_t* out_lo, uint16_t* out2_hi,
                                                          uint16_t* out2_lo, int B, long thw,
                                                          const long* __restrict__ batch_index,
-                                                         const float* const* __restrict__ peer_x, int cpp) {
+                                                         const float* const* __restrict__ peer_x, int cpp,
+                                                         const float* __restrict__ nmean,
+                                                         const float* __restrict__ nstd) {
   const long total = (long)B * thw;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long b = i / thw, p = i - b * thw;
@@ -699,6 +701,8 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* x, long ba
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       vv[j] = j < Cin ? s[(long)j * chan_stride] : 0.f;
+      // T.Normalize of the reference's GPU-side `tr` (main_nce.py:207-209, utils/transforms.py:57-63): (x - mean) / std
+      if (nmean != nullptr && j < Cin) vv[j] = __fdiv_rn(__fsub_rn(vv[j], nmean[j]), nstd[j]);
       split2<false>(vv[j], h[j], l[j]);
     }
     if (out2_hi != nullptr) {
@@ -723,7 +727,9 @@ __global__ void __launch_bounds__(256) pack_input_s2d_kernel(const float* x, lon
                                                              uint16_t* out_hi, uint16_t* out_lo,
                                                              uint16_t* out2_hi, uint16_t* out2_lo, int B, int T, int H,
                                                              int W, const long* __restrict__ batch_index,
-                                                             const float* const* __restrict__ peer_x, int cpp) {
+                                                             const float* const* __restrict__ peer_x, int cpp,
+                                                             const float* __restrict__ nmean,
+                                                             const float* __restrict__ nstd) {
   const int H2 = H >> 1, W2 = W >> 1;
   const long total = (long)B * T * H2 * W2;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -743,7 +749,11 @@ __global__ void __launch_bounds__(256) pack_input_s2d_kernel(const float* x, lon
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
       for (int c = 0; c < Cin; ++c) {
-        const float2 p2 = *reinterpret_cast<const float2*>(s + (long)c * chan_stride + dy * W);
+        float2 p2 = *reinterpret_cast<const float2*>(s + (long)c * chan_stride + dy * W);
+        if (nmean != nullptr) {   // fused T.Normalize, see pack_input_kernel
+          p2.x = __fdiv_rn(__fsub_rn(p2.x, nmean[c]), nstd[c]);
+          p2.y = __fdiv_rn(__fsub_rn(p2.y, nmean[c]), nstd[c]);
+        }
         vv[(dy * 2 + 0) * Cin + c] = p2.x;
         vv[(dy * 2 + 1) * Cin + c] = p2.y;
       }
@@ -1003,21 +1013,23 @@ extern "C" int coclr_avgpool_bwd(const float* dfeat, float* dA, int ld, int coff
 
 extern "C" int coclr_pack_input(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi, void* out_lo,
                                 void* out2_hi, void* out2_lo, int B, long thw, const long* batch_index,
-                                const void* const* peer_x, int clips_per_peer, coclr_stream_t stream) {
-  if ((!x && !peer_x) || !out_hi || Cin < 1 || Cin > 8) return COCLR_E_ARG;
+                                const void* const* peer_x, int clips_per_peer, const float* norm_mean,
+                                const float* norm_std, coclr_stream_t stream) {
+  if ((!x && !peer_x) || !out_hi || Cin < 1 || Cin > 8 || (!norm_mean != !norm_std)) return COCLR_E_ARG;
   if (peer_x && (!batch_index || clips_per_peer < 1)) return COCLR_E_ARG;
   pack_input_kernel<<<grid_for((long)B * thw, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
       x, batch_stride, chan_stride, Cin, reinterpret_cast<uint16_t*>(out_hi), reinterpret_cast<uint16_t*>(out_lo),
       reinterpret_cast<uint16_t*>(out2_hi), reinterpret_cast<uint16_t*>(out2_lo), B, thw, batch_index,
-      reinterpret_cast<const float* const*>(peer_x), clips_per_peer);
+      reinterpret_cast<const float* const*>(peer_x), clips_per_peer, norm_mean, norm_std);
   return LAUNCH_OK();
 }
 
 extern "C" int coclr_pack_input_s2d(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi,
                                     void* out_lo, void* out2_hi, void* out2_lo, int B, int T, int H, int W,
                                     const long* batch_index, const void* const* peer_x, int clips_per_peer,
-                                    coclr_stream_t stream) {
-  if ((!x && !peer_x) || !out_hi || Cin < 1 || Cin > 4 || (H & 1) || (W & 1)) return COCLR_E_ARG;
+                                    const float* norm_mean, const float* norm_std, coclr_stream_t stream) {
+  if ((!x && !peer_x) || !out_hi || Cin < 1 || Cin > 4 || (H & 1) || (W & 1) || (!norm_mean != !norm_std))
+    return COCLR_E_ARG;
   if (peer_x && (!batch_index || clips_per_peer < 1)) return COCLR_E_ARG;
   const long total = (long)B * T * (H / 2) * (W / 2);
   if ((batch_stride | chan_stride) & 1) return COCLR_E_ARG;  // 8-byte loads of (x, x+1) pairs
@@ -1025,7 +1037,7 @@ extern "C" int coclr_pack_input_s2d(const float* x, long batch_stride, long chan
   pack_input_s2d_kernel<CIN><<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(                    \
       x, batch_stride, chan_stride, reinterpret_cast<uint16_t*>(out_hi), reinterpret_cast<uint16_t*>(out_lo),       \
       reinterpret_cast<uint16_t*>(out2_hi), reinterpret_cast<uint16_t*>(out2_lo), B, T, H, W, batch_index,          \
-      reinterpret_cast<const float* const*>(peer_x), clips_per_peer)
+      reinterpret_cast<const float* const*>(peer_x), clips_per_peer, norm_mean, norm_std)
   switch (Cin) {
     case 1: COCLR_PACK_S2D(1); break;
     case 2: COCLR_PACK_S2D(2); break;

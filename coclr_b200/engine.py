@@ -762,18 +762,23 @@ class EncoderEngine:
             main.wait_stream(side)
         L.LAUNCHES += sum(L.KERNELS_PER_CALL.get(fn.__name__, 1) for fn, _ in oplist)
 
-    def forward(self, x, training=True, with_backward=False, repack=True, batch_index=None, batch=None, peers=None):
+    def forward(self, x, training=True, with_backward=False, repack=True, batch_index=None, batch=None, peers=None,
+                norm=None):
         """x: [*, C, T, H, W] fp32 CUDA (any batch stride). Clip b of the pass is x[batch_index[b]] when a
         device int64 index is given (shuffle-BN gather), else x[b].  peers = (device pointer of an array with one
         peer-mapped clip buffer per rank, clips per rank): batch_index then is a GLOBAL clip index and the clips are
-        read straight from the owning ranks' buffers (same layout as x) over NVLink.  Returns the plan; plan.q holds
+        read straight from the owning ranks' buffers (same layout as x) over NVLink.  norm = (mean, std) device fp32
+        [C]: per-channel (x - mean) / std applied while packing (the reference's GPU-side T.Normalize).  Only the three
+        innermost dims of x must be dense: batch and channel strides are free, so a clip may be a view into the loader's
+        [B, C, num_seq*seq_len, H, W] tensor.  Returns the plan; plan.q holds
         the normalised features [B, dim] (plan.backbone_out the backbone output when there is no head)."""
         if not x.is_cuda:
             raise L.CoclrError("coclr_b200 encoders run on CUDA only (no CPU fallback)")
         _, Cin, T, H, W = x.shape
         B = x.shape[0] if batch is None else batch
         assert Cin == self.graph.first_channel and x.dtype == torch.float32
-        assert x.stride(4) == 1 and x.stride(3) == W and x.stride(2) == H * W and x.stride(1) == T * H * W
+        assert x.stride(4) == 1 and x.stride(3) == W and x.stride(2) == H * W
+        nm, ns = (L.dptr(norm[0]), L.dptr(norm[1])) if norm is not None else (None, None)
         if batch_index is not None:
             assert batch_index.dtype == torch.long and batch_index.is_cuda and batch_index.numel() == B
         p = self.plan(B, T, H, W, training, with_backward)
@@ -787,12 +792,12 @@ class EncoderEngine:
             L.check(lib.coclr_pack_input_s2d(L.dptr(x), x.stride(0), x.stride(1), Cin, L.dptr(p.input.pl.hi),
                                              L.dptr(p.input.pl.lo), L.dptr(tw.hi) if tw else None,
                                              L.dptr(tw.lo) if tw else None, B, T, H, W, L.dptr(batch_index),
-                                             peer_ptr, cpp, L.stream_ptr()), "coclr_pack_input_s2d")
+                                             peer_ptr, cpp, nm, ns, L.stream_ptr()), "coclr_pack_input_s2d")
         else:
             L.check(lib.coclr_pack_input(L.dptr(x), x.stride(0), x.stride(1), Cin, L.dptr(p.input.pl.hi),
                                          L.dptr(p.input.pl.lo), L.dptr(tw.hi) if tw else None,
                                          L.dptr(tw.lo) if tw else None, B, T * H * W, L.dptr(batch_index),
-                                         peer_ptr, cpp, L.stream_ptr()), "coclr_pack_input")
+                                         peer_ptr, cpp, nm, ns, L.stream_ptr()), "coclr_pack_input")
 
         def body():
             if repack:

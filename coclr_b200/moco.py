@@ -65,7 +65,7 @@ class _EncodeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, anchor, enc, x, training):
-        plan = enc._engine_for(x.device).forward(x, training=training, with_backward=True)
+        plan = enc._engine_for(x.device).forward(x, training=training, with_backward=True, norm=enc.input_norm)
         ctx.enc, ctx.plan = enc, plan
         return plan.q.clone()
 
@@ -90,6 +90,7 @@ class MoCoEncoder(nn.Sequential):
         self.feature_size, self.dim, self.precision = feature_size, dim, precision
         self._engine = None
         self._anchor = None
+        self.input_norm = None   # (mean, std) device tensors: per-channel normalisation fused into the clip packing
 
     # -- engine -------------------------------------------------------------------------------
     def _engine_for(self, device):
@@ -128,7 +129,7 @@ class MoCoEncoder(nn.Sequential):
             assert batch_index is None
             return _EncodeFn.apply(self._anchor, self, x, self.training)
         plan = eng.forward(x, training=self.training, with_backward=False, batch_index=batch_index, batch=batch,
-                           peers=peers)
+                           peers=peers, norm=self.input_norm)
         return plan.q.clone()
 
     def forward(self, x):
@@ -136,7 +137,7 @@ class MoCoEncoder(nn.Sequential):
         eng = self._engine_for(x.device)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise L.CoclrError("use .encode() (autograd-aware) for training; forward() is inference-only")
-        plan = eng.forward(x, training=self.training, with_backward=False)
+        plan = eng.forward(x, training=self.training, with_backward=False, norm=self.input_norm)
         return (plan.h2.view(x.shape[0], self.dim) + self[4].bias).view(x.shape[0], self.dim, 1, 1, 1)
 
 

@@ -221,16 +221,23 @@ int coclr_avgpool_bwd(const float* dfeat, float* dA, int ld, int coff, int B, in
  * peer_x != NULL (device array of one clip-buffer base per rank, NVLink peer-mapped, clips_per_peer clips each; x is
  * then ignored): clip g = batch_index[b] is read from peer_x[g / clips_per_peer] + (g % clips_per_peer) * batch_stride,
  * i.e. the all-gather of every rank's clips (pretrain.py:105-106) is replaced by P2P loads of only the B clips this
- * rank encodes ------------------------------------------------------------------------------------------------ */
+ * rank encodes.
+ * norm_mean / norm_std != NULL: the per-channel (x - mean) / std of the reference's GPU-side input transform `tr`
+ * (T.Normalize, main_nce.py:207-209,299-302) is applied on the fly; together with the free batch / channel strides
+ * (the loader's [B, C, num_seq*seq_len, H, W] tensor is addressed in place) this folds `tr` -- normalise, view,
+ * transpose(1,2), contiguous -- into the packing pass ------------------------------------------------------- */
 int coclr_pack_input(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi, void* out_lo,
                      void* out2_hi, void* out2_lo /* optional bf16 twin */, int B, long thw, const long* batch_index,
-                     const void* const* peer_x, int clips_per_peer, coclr_stream_t stream);
+                     const void* const* peer_x, int clips_per_peer,
+                     const float* norm_mean, const float* norm_std /* device [Cin] or both NULL */,
+                     coclr_stream_t stream);
 
 /* space-to-depth variant for the stride-2 7x7 RGB stem (backbone/s3dg.py:145): planes [B, T, H/2, W/2, 16] with
  * channel (dy*2+dx)*Cin + c = x[b, c, t, 2Y+dy, 2X+dx] (4*Cin real channels, rest zero); H, W even */
 int coclr_pack_input_s2d(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi, void* out_lo,
                          void* out2_hi, void* out2_lo, int B, int T, int H, int W, const long* batch_index,
-                         const void* const* peer_x, int clips_per_peer, coclr_stream_t stream);
+                         const void* const* peer_x, int clips_per_peer, const float* norm_mean, const float* norm_std,
+                         coclr_stream_t stream);
 
 /* ---- F.normalize(z + bias, dim=1) (model/pretrain.py:154,167) ------------------------------------- */
 int coclr_l2norm_fwd(const float* z, const float* bias, float* q, float* inv_norm, int B, int D, coclr_stream_t stream);

@@ -70,6 +70,9 @@ def parse_args(argv=None):
     p.add_argument('--moco-t', default=0.07, type=float)
     # additions
     p.add_argument('--synthetic', action='store_true')
+    p.add_argument('--raw-input', action='store_true',
+                   help='feed the loader layout [B,3,num_seq*seq_len,H,W] in [0,1]; T.Normalize + view + transpose of the '
+                        'reference\'s GPU-side `tr` (main_nce.py:207-209,299-302) run fused in the clip-packing kernel')
     p.add_argument('--precision', default='parity', choices=['parity', 'mixed', 'fast'])
     p.add_argument('--steps-per-epoch', default=20, type=int)
     p.add_argument('--num-classes', default=101, type=int, help='label range of the synthetic UberNCE labels')
@@ -105,7 +108,10 @@ class SyntheticClips:
     def __iter__(self):
         a = self.args
         for _ in range(a.steps_per_epoch):
-            x = torch.randn(a.batch_size, 2, 3, a.seq_len, a.img_dim, a.img_dim, device=self.device, generator=self.gen)
+            if getattr(a, "raw_input", False):   # what the reference's DataLoader yields before `tr`
+                x = torch.rand(a.batch_size, 3, 2 * a.seq_len, a.img_dim, a.img_dim, device=self.device, generator=self.gen)
+            else:
+                x = torch.randn(a.batch_size, 2, 3, a.seq_len, a.img_dim, a.img_dim, device=self.device, generator=self.gen)
             y = torch.randint(0, a.num_classes, (a.batch_size,), device=self.device, generator=self.gen)
             yield x, y
 
@@ -207,6 +213,8 @@ def main_worker(args):
     random.seed(args.seed)
     cls = {'infonce': InfoNCE, 'ubernce': UberNCE}[args.model]
     model = cls(args.net, args.moco_dim, args.moco_k, args.moco_m, args.moco_t, precision=args.precision).to(device)
+    if args.raw_input:
+        model.set_input_transform(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])   # reference main_nce.py:207-209
     optimizer = moco.FlatAdam(model.encoder_q, lr=args.lr, weight_decay=args.wd)
     args.iteration = 1
     best_acc = 0.0

@@ -53,6 +53,36 @@ class InfoNCE(nn.Module):
         self._side_stream = None
         self._peer_clips = {}     # clip shape -> moco.PeerClips, or False when symmetric memory is unavailable
 
+    # -- fused input transform -----------------------------------------------------------------------
+    def set_input_transform(self, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+        """Fold the reference's GPU-side `tr` (main_nce.py:207-209,299-302: T.Normalize(mean, std, channel=1) ->
+        view(B,3,num_seq,seq_len,H,W) -> transpose(1,2) -> contiguous) into the clip-packing kernel.  After this call
+        forward() also accepts the loader's tensor as is -- [B, 3, num_seq*seq_len, H, W] in [0, 1] -- and every encoder
+        normalises on the fly; the [B, 2, 3, T, H, W] form is normalised the same way.  mean=None switches it off."""
+        self._input_tf = None if mean is None else (tuple(float(v) for v in mean), tuple(float(v) for v in std))
+        self._input_tf_dev = None
+        for enc in self._encoders():
+            enc.input_norm = None
+
+    def _encoders(self):
+        return [m for m in (self.encoder_q, self.encoder_k, getattr(self, "sampler", None)) if m is not None]
+
+    def _views(self, block):
+        """The two clips of a sample as [B, C, T, H, W] views (no copies): from [B, 2, C, T, H, W] (what the reference's
+        forward takes, pretrain.py:145-150) or from the loader layout [B, C, 2*T, H, W] (before `tr`)."""
+        tf = getattr(self, "_input_tf", None)
+        if tf is not None and getattr(self, "_input_tf_dev", None) is None:
+            self._input_tf_dev = (torch.tensor(tf[0], dtype=torch.float32, device=block.device),
+                                  torch.tensor(tf[1], dtype=torch.float32, device=block.device))
+            for enc in self._encoders():
+                enc.input_norm = self._input_tf_dev
+        if block.dim() == 5:
+            assert block.shape[2] % 2 == 0, "loader layout [B, C, 2*T, H, W] expected"
+            T = block.shape[2] // 2
+            return block[:, :, :T], block[:, :, T:]
+        assert block.shape[1] == 2                                                    # pretrain.py:148
+        return block[:, 0], block[:, 1]
+
     # -- queue pointer mirror ---------------------------------------------------------------------
     def _load_from_state_dict(self, *args, **kwargs):
         self._ptr_host = None  # re-read the loaded pointer lazily
@@ -127,11 +157,9 @@ class InfoNCE(nn.Module):
         return ptr
 
     def _qk(self, block):
-        (B, N, *_) = block.shape
-        assert N == 2                                                                 # pretrain.py:148
         if not block.is_cuda:
             raise moco.L.CoclrError("coclr_b200 modules run on CUDA (sm_100a) only; there is no CPU path")
-        x1, x2 = block[:, 0], block[:, 1]          # views; the .contiguous() copies are folded into packing
+        x1, x2 = self._views(block)                # views; the .contiguous() copies are folded into packing
         in_train_mode = torch.is_grad_enabled() and any(p.requires_grad for p in self.encoder_q.parameters())  # :157
         # the key branch (EMA -> shuffle -> encoder_k) does not depend on the query forward: run it on a side stream
         # so that the many small layers of the two encoders fill the SMs together
@@ -196,10 +224,8 @@ class CoCLR(InfoNCE):
         self.reverse = reverse
 
     def forward(self, block1, block2, k_vsource):
-        (B, N, *_) = block1.shape
-        assert N == 2
-        x1, f1 = block1[:, 0], block1[:, 1]
-        x2, f2 = block2[:, 0], block2[:, 1]
+        x1, f1 = self._views(block1)
+        x2, f2 = self._views(block2)
         if self.reverse:                                                              # :353-355
             x1, f1 = f1, x1
             x2, f2 = f2, x2

@@ -36,6 +36,12 @@ def test_main_nce_trains_saves_resumes(tmp_path, net, model):
     assert "Training from ep 2 to ep 3 finished" in out2
 
 
+def test_main_nce_raw_loader_input(tmp_path):
+    """--raw-input: the loader layout goes in unchanged, normalisation / clip split run inside the packing kernel."""
+    out = _run("main_nce.py", SMALL + ["--net", "s3d", "--model", "infonce", "--epochs", "1", "--raw-input"], str(tmp_path))
+    assert "Training from ep 0 to ep 1 finished" in out and "loss" in out and "nan" not in out.lower()
+
+
 def test_main_coclr_cycle(tmp_path):
     args = ["--synthetic", "--batch_size", "4", "--seq_len", "8", "--img_dim", "64", "--moco-k", "16", "--steps-per-epoch", "7",
             "--print_freq", "1", "--net", "s3d", "--epochs", "1", "--topk", "5"]
