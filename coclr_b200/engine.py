@@ -54,6 +54,10 @@ class ConvSpec:
         # what the kernels see; differs from the parameter's own shape only for the space-to-depth stem
         self.s2d = False
         self.cin_eff, self.k_eff, self.s_eff, self.p_eff = cin, k, s, p
+        # channel slice of the source tensor this conv reads (default: all of it)
+        self.src_coff, self.src_C = 0, src.C
+        # parameter names whose (adjacent) [cout_i, cin, 1, 1, 1] weights this conv uses as one [sum cout_i, cin] matrix
+        self.weight_names = [name]
 
 
 class PoolSpec:
@@ -86,8 +90,13 @@ class _LaneList(list):
 class Graph:
     """Shape-independent description of the encoder: tensors, convs, pools in forward order."""
 
+    # the 1x1x1 convs that open branches 1 and 2 of a SepInception read the same input: run them as ONE conv
+    # (N = o1a + o2a instead of e.g. 96 and 16 output channels) into one buffer that the two branches slice
+    fuse_b12_default = os.environ.get("COCLR_FUSE_B12", "1") != "0"
+
     def __init__(self, stages, first_channel=3, head_dim=None, feature_size=S3D_FEATURE_SIZE, bb_prefix="",
-                 stem_s2d=True):
+                 stem_s2d=True, fuse_b12=None):
+        self.fuse_b12 = Graph.fuse_b12_default if fuse_b12 is None else bool(fuse_b12)
         self.tensors, self.items = [], _LaneList(self)   # items: ("conv", ConvSpec) | ("pool", PoolSpec) | ("bn", TensorSpec)
         self.item_lane, self.item_flag = [], []   # per item: stream lane (Inception branches run concurrently) and FORK/JOIN
         self.cur_lane, self.next_flag = 0, 0
@@ -174,12 +183,14 @@ class Graph:
         self.items.append(("conv", c))
         return c
 
-    def _st(self, name, x, dst, dst_coff, cin, cout, k, ss, ts, pad, need_dgrad=True):
+    def _st(self, name, x, dst, dst_coff, cin, cout, k, ss, ts, pad, need_dgrad=True, src_coff=0):
         k1, s1, p1 = (1, k, k), (1, ss, ss), (0, pad, pad)
         k2, s2, p2 = (k, 1, 1), (ts, 1, 1), (pad, 0, 0)
         s2d = (not need_dgrad) and self.stem_s2d and x is self.input
         mid = self._tensor(name + ".mid", cout, self._same(x) if s2d else self._after(x, k1, s1, p1))
         cv = self._conv(name + ".conv1", x, mid, 0, cin, cout, k1, s1, p1, need_dgrad=need_dgrad)
+        if src_coff or cin != x.C and x is not self.input:
+            cv.src_coff, cv.src_C = src_coff, cin
         if s2d:
             cv.s2d, cv.cin_eff, cv.k_eff, cv.s_eff, cv.p_eff = True, 4 * cin, (1, 4, 4), (1, 1, 1), (0, 2, 2)
         mid.bn_members.append((name + ".bn1", 0, cout))
@@ -202,6 +213,26 @@ class Graph:
         o0, o1a, o1b, o2a, o2b, o3b = planes
         cat = self._tensor(name, o0 + o1b + o2b + o3b, self._same(x))
         one = ((1, 1, 1), (1, 1, 1), (0, 0, 0))
+        if self.fuse_b12:
+            t12 = self._tensor(name + ".b12a", o1a + o2a, self._same(x))
+            cv = self._conv(name + ".branch1.0.conv", x, t12, 0, cin, o1a + o2a, *one)
+            cv.weight_names, cv.couts = [name + ".branch1.0.conv", name + ".branch2.0.conv"], [o1a, o2a]
+            t12.bn_members += [(name + ".branch1.0.bn", 0, o1a), (name + ".branch2.0.bn", o1a, o2a)]
+            self.items.append(("bn", t12))
+            self.cur_lane, self.next_flag = 0, FORK
+            self._conv(name + ".branch0.0.conv", x, cat, 0, cin, o0, *one)
+            cat.bn_members.append((name + ".branch0.0.bn", 0, o0))
+            self.cur_lane = 1
+            self._st(name + ".branch1.1", t12, cat, o0, o1a, o1b, 3, 1, 1, 1, src_coff=0)
+            self.cur_lane = 2
+            self._st(name + ".branch2.1", t12, cat, o0 + o1b, o2a, o2b, 3, 1, 1, 1, src_coff=o1a)
+            self.cur_lane = 3
+            tp = self._pool(name + ".branch3.0", x, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+            self._conv(name + ".branch3.1.conv", tp, cat, o0 + o1b + o2b, cin, o3b, *one)
+            cat.bn_members.append((name + ".branch3.1.bn", o0 + o1b + o2b, o3b))
+            self.cur_lane, self.next_flag = 0, JOIN
+            self.items.append(("bn", cat))
+            return cat
         self.cur_lane, self.next_flag = 0, FORK     # the four branches only share the (read-only) input planes
         self._conv(name + ".branch0.0.conv", x, cat, 0, cin, o0, *one)
         cat.bn_members.append((name + ".branch0.0.bn", 0, o0))
@@ -261,7 +292,11 @@ class Graph:
         out = []
         for kind, it in self.items:
             if kind == "conv":
-                out.append((it.name + ".weight", (it.cout, it.cin) + tuple(it.k)))
+                if len(it.weight_names) == 1:
+                    out.append((it.name + ".weight", (it.cout, it.cin) + tuple(it.k)))
+                else:   # fused convs: the member weights follow each other in the flat buffer (see ParamStore.view_span)
+                    for wn, co in zip(it.weight_names, it.couts):
+                        out.append((wn + ".weight", (co, it.cin) + tuple(it.k)))
         for kind, it in self.items:
             if kind == "bn":
                 for nm, _, c in it.bn_members:
@@ -316,6 +351,17 @@ class ParamStore:
     def view(self, name, grad=False):
         off, n, shape = self.offsets[name]
         return (self.grad if grad else self.flat)[off:off + n].view(shape)
+
+    def view_span(self, names, grad=False):
+        """One [sum cout_i, cin, kt, kh, kw] view over parameters that follow each other without gaps in the flat buffer."""
+        off0, _, shape0 = self.offsets[names[0]]
+        end, rows = off0, 0
+        for nm in names:
+            off, n, shape = self.offsets[nm]
+            if off != end or tuple(shape[1:]) != tuple(shape0[1:]):
+                raise RuntimeError("parameters %s are not adjacent in the flat buffer" % (names,))
+            end, rows = off + n, rows + shape[0]
+        return (self.grad if grad else self.flat)[off0:end].view((rows,) + tuple(shape0[1:]))
 
     def bind_module(self, named_params, named_buffers, prefix_map=lambda n: n):
         """Copy the module's current values in and rebind every Parameter / BN buffer to a view."""
@@ -404,8 +450,19 @@ class Plan:
         self.input = acts[g.input.index]
         st = eng.store
 
-        def src_of(a):
-            return a.pl.src(0, a.spec.C, a.dims[0], a.dims[1], a.dims[2])
+        def src_of(a, it=None):
+            coff, cc = (it.src_coff, it.src_C) if it is not None else (0, a.spec.C)
+            return a.pl.src(coff, cc, a.dims[0], a.dims[1], a.dims[2])
+
+        # which channel ranges of a tensor's gradient buffer already hold a value (first writer stores, later ones add)
+        grad_ranges = {}
+
+        def grad_seen(a, coff=0, cc=None):
+            key = (coff, a.spec.C if cc is None else cc)
+            seen = key in grad_ranges.setdefault(a.spec.index, set()) or (0, a.spec.C) in grad_ranges[a.spec.index]
+            grad_ranges[a.spec.index].add(key)
+            a.grad_written = True
+            return seen
 
         def twin_ptrs(pl, plw):
             if plw is None or plw is pl:
@@ -429,7 +486,7 @@ class Plan:
                 sa, da = acts[it.src.index], acts[it.dst.index]
                 geom = ops.Geometry(it.k_eff, it.s_eff, it.p_eff)
                 pw = eng.packed_fwd[it.name]
-                cv = ops.make_conv(src_of(sa), fbf, geom.c(0), B, da.dims, pw, da.data, it.dst_coff,
+                cv = ops.make_conv(src_of(sa, it), fbf, geom.c(0), B, da.dims, pw, da.data, it.dst_coff,
                                    stats_sum=da.ssum[it.dst_coff:] if training else None,
                                    stats_sq=da.ssq[it.dst_coff:] if training else None, npass=fnp)
                 self.keep.append(cv)
@@ -525,7 +582,7 @@ class Plan:
             bw.append((lib.coclr_conv_wgrad, (C.byref(wg1),)))
             bw.append((lib.coclr_conv_igemm, (C.byref(dg1), nsm)))
             bw.append((lib.coclr_avgpool_bwd, (L.dptr(self.dfeat), L.dptr(out.grad), out.spec.C, 0, B, Pn, fs)))
-            out.grad_written = True
+            grad_seen(out)
         convs_into, pool_into = {}, {}
         for kind, it in g.items:
             if kind == "conv":
@@ -548,8 +605,7 @@ class Plan:
                 if t.residual is not None:
                     ra = acts[t.residual.index]
                     res_args = (L.dptr(ra.pl.hi), L.dptr(ra.pl.lo), ra.pl.ld, 0, ra.pl.bf16,
-                                L.dptr(ra.grad), ra.spec.C, 0, int(ra.grad_written))
-                    ra.grad_written = True
+                                L.dptr(ra.grad), ra.spec.C, 0, int(grad_seen(ra)))
                 else:
                     res_args = (None, None, 0, 0, 0, None, 0, 0, 0)
                 bb = L.BnBwd(L.dptr(a.data), L.dptr(a.grad), t.C, 0, t.C, a.M, L.dptr(a.scale), L.dptr(a.shift),
@@ -561,7 +617,7 @@ class Plan:
                     sa = acts[it.src.index]
                     geom = ops.Geometry(it.k_eff, it.s_eff, it.p_eff)
                     dy = a.dy.src(it.dst_coff, _round8(it.cout), a.dims[0], a.dims[1], a.dims[2])
-                    kreal = geom.taps * it.src.C
+                    kreal = geom.taps * it.src_C
                     kt = (kreal + 255) // 256
                     bnk = (((kreal + kt - 1) // kt) + 63) // 64 * 64
                     tiles = ((kreal + bnk - 1) // bnk) * ((it.cout + 127) // 128)
@@ -570,7 +626,7 @@ class Plan:
                     # ... and every split should own >= 16 pixel chunks: each split ends with Cout x K fp32 atomics,
                     # which dominate when the pixel range per CTA is short
                     splits = max(1, min(chunks // 16 if chunks >= 16 else 1, (2 * nsm) // tiles))
-                    wsrc = sa.plw.src(0, sa.spec.C, sa.dims[0], sa.dims[1], sa.dims[2])
+                    wsrc = sa.plw.src(it.src_coff, it.src_C, sa.dims[0], sa.dims[1], sa.dims[2])
                     if it.s2d:
                         # the weight gradient is produced in the space-to-depth layout, then scattered back
                         dw_eff = eng.s2d[it.name]["dw_eff"]
@@ -580,25 +636,24 @@ class Plan:
                         bw.append((eng._s2d_wgrad_op(it.name, wg), ()))
                     else:
                         wg = L.Wgrad(wsrc, geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin,
-                                     L.dptr(st.view(it.name + ".weight", grad=True)), bnp, 1, 1, splits)
+                                     L.dptr(st.view_span([n + ".weight" for n in it.weight_names], grad=True)), bnp, 1, 1,
+                                     splits)
                         self.keep += [wg, dy]
                         bw.append((lib.coclr_conv_wgrad, (C.byref(wg),)))
                     if it.need_dgrad:
-                        dg = ops.make_conv(dy, 1, geom.c(1), B, sa.dims, eng.packed_bwd[it.name], sa.grad, 0,
-                                           accumulate=sa.grad_written, npass=bnp)
+                        dg = ops.make_conv(dy, 1, geom.c(1), B, sa.dims, eng.packed_bwd[it.name], sa.grad, it.src_coff,
+                                           accumulate=grad_seen(sa, it.src_coff, it.src_C), npass=bnp)
                         self.keep.append(dg)
                         bw.append((lib.coclr_conv_igemm, (C.byref(dg), nsm)))
-                        sa.grad_written = True
             elif t.index in pool_into:
                 it = pool_into[t.index]
                 sa = acts[it.src.index]
                 geom = ops.Geometry(it.k, it.s, it.p)
                 pl = L.Pool(None, None, it.src.C, 0, None, None, t.C, 0, None, None, L.dptr(a.idx), B, t.C,
                             sa.dims[0], sa.dims[1], sa.dims[2], a.dims[0], a.dims[1], a.dims[2], geom.c(0),
-                            L.dptr(a.grad), L.dptr(sa.grad), int(sa.grad_written))
+                            L.dptr(a.grad), L.dptr(sa.grad), int(grad_seen(sa)))
                 self.keep.append(pl)
                 bw.append((lib.coclr_maxpool_bwd, (C.byref(pl),)))
-                sa.grad_written = True
 
 
 class EncoderEngine:
@@ -618,10 +673,10 @@ class EncoderEngine:
             if kind != "conv":
                 continue
             taps = it.k_eff[0] * it.k_eff[1] * it.k_eff[2]
-            w = store.view(it.name + ".weight")
+            w = store.view_span([n + ".weight" for n in it.weight_names])
             if it.s2d:
                 w = self._make_s2d(it, w, dev)
-            pf = ops.PackedWeights(it.cout, it.cin_eff, taps, it.src.C, 0, fbf, dev)
+            pf = ops.PackedWeights(it.cout, it.cin_eff, taps, it.src_C, 0, fbf, dev)
             self.packed_fwd[it.name] = pf
             self._packs.append((pf, w, False))
             if it.need_dgrad:

@@ -77,8 +77,8 @@ def test_graph_covers_reference_parameters():
     rm = {k[len("encoder_q."):-len(".running_mean")]: v[0] for k, v in O.infonce_shapes(128, 128).items()
           if k.startswith("encoder_q.") and k.endswith(".running_mean")}
     assert bufs == rm
-    # 77 backbone convs, 13 pools
-    assert sum(1 for k, _ in g.items if k == "conv") == 77
+    # 77 backbone convs (the 9 pairs of branch-opening 1x1 convs may run as one launch each), 13 pools
+    assert sum(len(it.weight_names) for k, it in g.items if k == "conv") == 77
     assert sum(1 for k, _ in g.items if k == "pool") == 13
     # shapes at 32 x 128^2
     dims = g.backbone_out.dims_fn((32, 128, 128))
@@ -113,14 +113,24 @@ def test_launch_plans_build_on_cpu_dry_run():
         eng = EncoderEngine(st, g, "parity")
         p = eng.plan(2, 8, 64, 64, True, True)
         names = [fn.__name__ for fn, _ in p.fwd]
-        assert names.count("coclr_conv_igemm") == 77 + 2
+        fused = 9 if g.fuse_b12 else 0    # per SepInception: branch1.0 + branch2.0 1x1 convs run as one conv, one BN pass
+        assert names.count("coclr_conv_igemm") == 77 - fused + 2
         assert names.count("coclr_maxpool_fwd") == 13
-        assert names.count("coclr_affine_split") == (77 - 9 * 3) + 2   # one fused BN-finalize+apply+split per tensor (concat tensors hold 4 BNs) + 2 head splits
+        assert names.count("coclr_affine_split") == (77 - 9 * 3) - fused + 2   # one fused BN-finalize+apply+split per tensor (concat tensors hold 4 BNs) + 2 head splits
         bn = [fn.__name__ for fn, _ in p.bwd]
-        assert bn.count("coclr_conv_wgrad") + bn.count("coclr_conv_wgrad_s2d") == 77 + 2   # the stem's runs in space-to-depth form
-        assert bn.count("coclr_conv_igemm") == 76 + 2           # no dgrad for the RGB stem conv
+        assert bn.count("coclr_conv_wgrad") + bn.count("coclr_conv_wgrad_s2d") == 77 - fused + 2   # the stem's runs in space-to-depth form
+        assert bn.count("coclr_conv_igemm") == 76 - fused + 2   # no dgrad for the RGB stem conv
         assert bn.count("coclr_maxpool_bwd") == 13
-        assert bn.count("coclr_bn_bwd") == 77 - 9 * 3
+        assert bn.count("coclr_bn_bwd") == 77 - 9 * 3 - fused
+        # fused 1x1 convs: member weights / BN parameters adjacent in the flat buffer, consumers read channel slices
+        for kind, it in g.items:
+            if kind == "conv" and len(it.weight_names) == 2:
+                w = st.view_span([n + ".weight" for n in it.weight_names])
+                assert w.shape[0] == sum(it.couts) and w.data_ptr() == st.view(it.weight_names[0] + ".weight").data_ptr()
+        sliced = [it for kind, it in g.items if kind == "conv" and it.src_C != it.src.C and it.src is not g.input]
+        assert len(sliced) == 2 * fused and all(it.src_coff % 8 == 0 and it.src_C % 8 == 0 for it in sliced)
+        g0 = Graph(s3d_stages(3), 3, head_dim=128, bb_prefix="0.", fuse_b12=False)
+        assert [n for n, _ in g0.param_layout()] != [] and sorted(n for n, _ in g0.param_layout()) == sorted(n for n, _ in g.param_layout())
         # inference plan has no gradient buffers
         p2 = eng.plan(2, 8, 64, 64, True, False)
         assert not p2.bwd and all(a.grad is None for a in p2.acts.values())
