@@ -69,7 +69,7 @@ def _conv_out(d, k, s, p):
     return (d + 2 * p - k) // s + 1
 
 
-FORK, JOIN = 1, 2
+FORK, JOIN, AFTER1 = 1, 2, 3   # AFTER1: the item's lane first waits for what lane 1 has been given so far
 
 
 class _LaneList(list):
@@ -215,17 +215,18 @@ class Graph:
         one = ((1, 1, 1), (1, 1, 1), (0, 0, 0))
         if self.fuse_b12:
             t12 = self._tensor(name + ".b12a", o1a + o2a, self._same(x))
+            self.cur_lane, self.next_flag = 1, FORK     # lane 1: fused 1x1 conv + its BN, then branch 1
             cv = self._conv(name + ".branch1.0.conv", x, t12, 0, cin, o1a + o2a, *one)
             cv.weight_names, cv.couts = [name + ".branch1.0.conv", name + ".branch2.0.conv"], [o1a, o2a]
             t12.bn_members += [(name + ".branch1.0.bn", 0, o1a), (name + ".branch2.0.bn", o1a, o2a)]
             self.items.append(("bn", t12))
-            self.cur_lane, self.next_flag = 0, FORK
-            self._conv(name + ".branch0.0.conv", x, cat, 0, cin, o0, *one)
-            cat.bn_members.append((name + ".branch0.0.bn", 0, o0))
+            self.cur_lane, self.next_flag = 2, AFTER1   # lane 2: branch 2 starts once the shared buffer is ready
+            self._st(name + ".branch2.1", t12, cat, o0 + o1b, o2a, o2b, 3, 1, 1, 1, src_coff=o1a)
             self.cur_lane = 1
             self._st(name + ".branch1.1", t12, cat, o0, o1a, o1b, 3, 1, 1, 1, src_coff=0)
-            self.cur_lane = 2
-            self._st(name + ".branch2.1", t12, cat, o0 + o1b, o2a, o2b, 3, 1, 1, 1, src_coff=o1a)
+            self.cur_lane = 0
+            self._conv(name + ".branch0.0.conv", x, cat, 0, cin, o0, *one)
+            cat.bn_members.append((name + ".branch0.0.bn", 0, o0))
             self.cur_lane = 3
             tp = self._pool(name + ".branch3.0", x, (3, 3, 3), (1, 1, 1), (1, 1, 1))
             self._conv(name + ".branch3.1.conv", tp, cat, o0 + o1b + o2b, cin, o3b, *one)
@@ -777,6 +778,8 @@ class EncoderEngine:
             if lane != 0 and lane not in active:
                 self._lane_streams[lane].wait_event(fork_ev)
                 active.add(lane)
+            if flag == AFTER1:
+                (self._lane_streams[lane] if lane else main).wait_stream(self._lane_streams[1])
             rc = fn(*args, ptrs[lane])
             if rc != 0:
                 raise L.CoclrError("%s failed with code %d" % (fn.__name__, rc))
