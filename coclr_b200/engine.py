@@ -231,6 +231,9 @@ class Graph:
             tp = self._pool(name + ".branch3.0", x, (3, 3, 3), (1, 1, 1), (1, 1, 1))
             self._conv(name + ".branch3.1.conv", tp, cat, o0 + o1b + o2b, cin, o3b, *one)
             cat.bn_members.append((name + ".branch3.1.bn", o0 + o1b + o2b, o3b))
+            # the branches were issued out of channel order; the per-tensor BatchNorm needs its members' parameters laid
+            # out in channel order (one gamma / beta vector for the whole concat buffer)
+            cat.bn_members.sort(key=lambda m: m[1])
             self.cur_lane, self.next_flag = 0, JOIN
             self.items.append(("bn", cat))
             return cat

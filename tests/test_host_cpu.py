@@ -127,6 +127,12 @@ def test_launch_plans_build_on_cpu_dry_run():
             if kind == "conv" and len(it.weight_names) == 2:
                 w = st.view_span([n + ".weight" for n in it.weight_names])
                 assert w.shape[0] == sum(it.couts) and w.data_ptr() == st.view(it.weight_names[0] + ".weight").data_ptr()
+        for t in g.tensors:     # per-tensor BatchNorm: members tile the channels in order, parameters follow that order
+            if t.bn_members:
+                assert [m[1] for m in t.bn_members] == sorted(m[1] for m in t.bn_members), t.name
+                assert sum(m[2] for m in t.bn_members) == t.C and t.bn_members[0][1] == 0
+                offs = [st.offsets[m[0] + ".weight"][0] for m in t.bn_members]
+                assert offs == sorted(offs) and offs[-1] - offs[0] == sum(m[2] for m in t.bn_members[:-1]), t.name
         sliced = [it for kind, it in g.items if kind == "conv" and it.src_C != it.src.C and it.src is not g.input]
         assert len(sliced) == 2 * fused and all(it.src_coff % 8 == 0 and it.src_C % 8 == 0 for it in sliced)
         g0 = Graph(s3d_stages(3), 3, head_dim=128, bb_prefix="0.", fuse_b12=False)
