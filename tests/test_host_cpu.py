@@ -175,3 +175,52 @@ def test_r50_plan_structure_dry_run():
         assert len(res) == 16 and sum(1 for t in res if t.residual.name.endswith(".ds")) == 4
     finally:
         L.DRY_RUN = False
+
+
+@pytest.mark.parametrize("stem", ["s3d", "r50"])
+def test_space_to_depth_stem_is_the_same_convolution(stem):
+    """Host logic of the space-to-depth stem (EncoderEngine._make_s2d + the layout coclr_pack_input_s2d writes): the
+    stride-1 (kt,4,4) conv over 2x2-blocked pixels with the gathered weight equals the reference's stride-2 (kt,7,7)
+    conv (backbone/s3dg.py:145 Conv_1a.conv1; backbone/resnet_2d3d.py:138 conv1), and the scatter-back of its weight
+    gradient equals the original conv's weight gradient.  Pure torch on the CPU."""
+    import torch.nn.functional as F
+    from coclr_b200 import lib as L
+    from coclr_b200.engine import Graph, ParamStore, EncoderEngine
+    from coclr_b200.s3d_spec import s3d_stages
+    from coclr_b200.r50_spec import r50_stages
+    L.DRY_RUN = True
+    try:
+        if stem == "s3d":
+            g = Graph(s3d_stages(3), 3, head_dim=None)
+            name, k, s, p = "Conv_1a.conv1", (1, 7, 7), (1, 2, 2), (0, 3, 3)
+        else:
+            g = Graph(r50_stages(3), 3, head_dim=None, feature_size=2048)
+            name, k, s, p = "conv1", (5, 7, 7), (2, 2, 2), (2, 3, 3)
+        st = ParamStore(g, torch.device("cpu"))
+        eng = EncoderEngine(st, g, "parity")
+    finally:
+        L.DRY_RUN = False
+    gen = torch.Generator().manual_seed(3)
+    w = st.view(name + ".weight")
+    w.copy_(torch.randn(w.shape, generator=gen) * 0.1)
+    eng._refresh_s2d()
+    d = eng.s2d[name]
+    w_eff = d["w_eff"].clone().requires_grad_(True)                 # [64, 12, kt, 4, 4]
+    B, T, H, W = 2, 6, 16, 12
+    x = torch.randn(B, 3, T, H, W, generator=gen)
+    # what coclr_pack_input_s2d writes: out[b, t, Y, X, (dy*2+dx)*Cin + c] = x[b, c, t, 2Y+dy, 2X+dx]
+    xs = x.view(B, 3, T, H // 2, 2, W // 2, 2).permute(0, 4, 6, 1, 2, 3, 5).reshape(B, 12, T, H // 2, W // 2)
+    wr = w.detach().clone().requires_grad_(True)
+    y_ref = F.conv3d(x, wr, stride=s, padding=p)
+    y_s2d = F.conv3d(xs, w_eff, stride=(s[0], 1, 1), padding=(p[0], 2, 2))[:, :, :, :H // 2, :W // 2]
+    assert y_ref.shape == y_s2d.shape
+    assert float((y_ref - y_s2d).abs().max()) < 1e-4 * float(y_ref.abs().max())
+    # backward: gradient w.r.t. the gathered weight, scattered back the way _s2d_wgrad_op does
+    dy = torch.randn(y_ref.shape, generator=gen)
+    y_ref.backward(dy)
+    y_s2d.backward(dy)
+    dw = torch.zeros(wr.numel()).index_add_(0, d["idx"], w_eff.grad.reshape(-1) * d["mask"]).view_as(wr)
+    assert float((dw - wr.grad).abs().max()) < 1e-4 * float(wr.grad.abs().max())
+    # the map is one-to-one on the 7x7 taps: every original weight is used exactly once
+    used = torch.zeros(wr.numel()).index_add_(0, d["idx"], d["mask"])
+    assert torch.equal(used, torch.ones_like(used))
