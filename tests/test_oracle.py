@@ -140,3 +140,23 @@ def test_oracle_r50_bitwise_vs_reference():
     assert set(msd.keys()) == set(sd.keys())
     for k, v in sd.items():
         assert _rel(v.detach().numpy(), msd[k].numpy()) < 1e-6, k
+
+
+def test_oracle_adam_is_torch_optim_adam():
+    """oracle.adam_step restates torch.optim.Adam(params, lr, weight_decay) as the reference builds it
+    (main_nce.py:190-200: one group, lr 1e-3, wd 1e-5, coupled L2): several steps on random tensors, bit-for-bit."""
+    g = torch.Generator().manual_seed(4)
+    shapes = [(64, 3, 1, 7, 7), (192,), (128, 1024, 1, 1, 1), (17,)]
+    ps = [torch.randn(s, generator=g) * 0.1 for s in shapes]
+    ref_params = [torch.nn.Parameter(p.clone()) for p in ps]
+    opt = torch.optim.Adam([{"params": ref_params}], lr=1e-3, weight_decay=1e-5)
+    mine = {str(i): p.clone() for i, p in enumerate(ps)}
+    state = {}
+    for step in range(5):
+        grads = [torch.randn(s, generator=g) * (0.01 + 0.1 * step) for s in shapes]
+        for p, gr in zip(ref_params, grads):
+            p.grad = gr.clone()
+        opt.step()
+        O.adam_step(mine, {str(i): gr for i, gr in enumerate(grads)}, state, lr=1e-3, weight_decay=1e-5)
+        for i, p in enumerate(ref_params):
+            assert torch.equal(mine[str(i)], p.detach()), (step, i)
