@@ -33,6 +33,8 @@ def parse_args(argv=None):
             extra["topk"] = int(argv[i + 1]); i += 2
         elif a == '--reverse':
             extra["reverse"] = True; i += 1
+        elif a == '--cos':      # accepted and unused, exactly as in the reference (main_coclr.py:92-93, never read)
+            i += 1
         elif a == '--pretrain':
             extra["pretrain"] = [argv[i + 1], argv[i + 2]]; i += 3
         else:

@@ -224,3 +224,34 @@ def test_space_to_depth_stem_is_the_same_convolution(stem):
     # the map is one-to-one on the 7x7 taps: every original weight is used exactly once
     used = torch.zeros(wr.numel()).index_add_(0, d["idx"], d["mask"])
     assert torch.equal(used, torch.ones_like(used))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference not mounted")
+def test_cli_accepts_every_reference_flag():
+    """Drop-in command line: every option of the reference's main_nce.py / main_coclr.py parses here, with the same
+    default for the options that shape the hot path."""
+    import main_nce
+    import main_coclr
+
+    def ref_flags(path):
+        out = {}
+        for m in re.finditer(r"add_argument\(([^)]*)\)", open(path).read()):
+            names = re.findall(r"'(-{1,2}[\w-]+)'", m.group(1))
+            takes_value = "store_true" not in m.group(1)
+            nargs2 = "nargs=2" in m.group(1)
+            for n in names:
+                out[n] = (takes_value, nargs2)
+        return out
+
+    for mod, path in ((main_nce, "/root/reference/main_nce.py"), (main_coclr, "/root/reference/main_coclr.py")):
+        for flag, (takes_value, nargs2) in ref_flags(path).items():
+            argv = [flag] + ((["a", "b"] if nargs2 else ["1"]) if takes_value else [])
+            try:
+                mod.parse_args(argv)
+            except SystemExit:
+                pytest.fail("%s does not accept %s" % (mod.__name__, flag))
+    a = main_nce.parse_args([])
+    assert (a.net, a.model, a.batch_size, a.seq_len, a.num_seq, a.img_dim, a.lr, a.wd) == ("s3d", "infonce", 32, 32, 2, 128, 1e-3, 1e-5)
+    assert (a.moco_dim, a.moco_k, a.moco_m, a.moco_t, a.schedule) == (128, 2048, 0.999, 0.07, [120, 160])
+    c = main_coclr.parse_args([])
+    assert (c.topk, c.reverse, c.model, c.dataset) == (5, False, "coclr", "ucf101-2stream-2clip")
