@@ -255,3 +255,30 @@ def test_cli_accepts_every_reference_flag():
     assert (a.moco_dim, a.moco_k, a.moco_m, a.moco_t, a.schedule) == (128, 2048, 0.999, 0.07, [120, 160])
     c = main_coclr.parse_args([])
     assert (c.topk, c.reverse, c.model, c.dataset) == (5, False, "coclr", "ucf101-2stream-2clip")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference not mounted")
+def test_training_losses_are_the_reference_formulas():
+    """The two mask losses of the training loops, executed from the reference's own source text (its scripts cannot be
+    imported: tensorboardX / lmdb are absent): multi_nce_loss (main_coclr.py:343-346) and the UberNCE loss lines
+    (main_nce.py:321-322) against main_coclr.multi_nce_loss / main_nce.multi_label_nce_loss, bit-for-bit."""
+    import ast
+    import torch.nn.functional as F
+    import main_nce
+    import main_coclr
+    src = open("/root/reference/main_coclr.py").read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "multi_nce_loss"][0]
+    ns = {"torch": torch, "F": F}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "ref_multi_nce_loss", "exec"), ns)
+    lines = open("/root/reference/main_nce.py").read().splitlines()
+    uber = [ln.strip() for ln in lines if ln.strip().startswith("loss = - (F.log_softmax(output, dim=1) * target)")]
+    assert len(uber) == 1
+    g = torch.Generator().manual_seed(9)
+    for _ in range(3):
+        logits = torch.randn(6, 1 + 40, generator=g) * 4
+        mask = torch.rand(6, 41, generator=g) < 0.15
+        mask[:, 0] = True
+        assert torch.equal(main_coclr.multi_nce_loss(logits, mask), ns["multi_nce_loss"](logits, mask))
+        env = {"F": F, "output": logits, "target": mask}
+        exec(uber[0], env)
+        assert torch.equal(main_nce.multi_label_nce_loss(logits, mask), env["loss"].mean())
