@@ -78,3 +78,93 @@ def test_shuffle_matches_oracle_simulated_world():
     k_sh = [_fake_encode(x_all[idx_shuffle.view(W, -1)[r]]) for r in range(W)]
     k_global = torch.cat(k_sh, 0)[idx_unshuffle]
     assert torch.allclose(k_global, _fake_encode(x_all), atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# UberNCE / CoCLR at world size 2: label / video-id / second-view key gathers and the integer queues
+# (model/pretrain.py:211-227, 321-341) -- host logic only, kernels replaced by torch stand-ins as above
+# ---------------------------------------------------------------------------------------------------------------
+def _stub_kernels(m, moco):
+    for enc in (m.encoder_q, m.encoder_k, getattr(m, "sampler", None)):
+        if enc is not None:
+            enc.encode = lambda x, batch_index=None, batch=None, peers=None: _fake_encode(x[batch_index] if batch_index is not None else x)
+    moco.enqueue = lambda queue, keys, ptr: queue.__setitem__((slice(None), slice(ptr, ptr + keys.shape[0])), keys.T)
+    moco.momentum_update = lambda q, k, mm: None
+    moco.nce_logits = lambda q, k, queue, T: torch.cat([(q * k).sum(1, keepdim=True), q @ queue.clone()], 1) / T
+
+
+def _worker_ext(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from model import pretrain as P
+    from coclr_b200 import moco
+    B, K = 4, 32
+    g = torch.Generator().manual_seed(300 + rank)
+    res = {}
+    # ---- UberNCE: forward() with the CUDA guard lifted (the stand-ins run on the CPU) ----
+    torch.manual_seed(0)
+    u = P.UberNCE("s3d", 128, K)
+    _stub_kernels(u, moco)
+    u.queue_label[:16] = torch.arange(16) % 5
+    block = torch.randn(B, 2, 3, 2, 8, 8, generator=g)
+    label = torch.randint(0, 5, (B,), generator=g)
+    def qk_cpu(self, block):       # InfoNCE._qk without its CUDA stream handling (the stand-ins run on the CPU)
+        x1, x2 = self._views(block)
+        with torch.no_grad():
+            self._momentum_update_key_encoder()
+            k, k_global = self._shuffled_keys(x2)
+        return self.encoder_q.encode(x1), k, k_global, True
+    P.InfoNCE._qk = qk_cpu
+    if True:
+        torch.manual_seed(11 + rank)
+        logits, mask = u(block, label)
+        res["u_mask"], res["u_queue_label"], res["u_ptr"] = mask.clone(), u.queue_label.clone(), int(u.queue_ptr)
+        res["u_label"], res["u_logits"] = label, logits.detach().clone()
+        # ---- CoCLR ----
+        torch.manual_seed(0)
+        c = P.CoCLR("s3d", 128, K, topk=3)
+        _stub_kernels(c, moco)
+        c.encoder_q.encode = lambda x, **kw: _fake_encode(x) * torch.ones(1, requires_grad=True)   # q must require grad (train mode)
+        c.queue_label[:] = 1                                     # queue full -> top-k branch
+        c.queue_vname[:] = torch.arange(K) % 7
+        b1 = torch.randn(B, 2, 3, 2, 8, 8, generator=g)
+        b2 = torch.randn(B, 2, 3, 2, 8, 8, generator=g)
+        vname = torch.randint(0, 7, (B,), generator=g)
+        torch.manual_seed(21 + rank)
+        lg, mk = c(b1, b2, vname)
+        res.update(c_mask=mk.clone(), c_queue_vname=c.queue_vname.clone(), c_queue_second=c.queue_second.clone(),
+                   c_queue=c.queue.clone(), c_ptr=int(c.queue_ptr), c_vname=vname, c_f2=b2[:, 1].clone(), c_x2=b2[:, 0].clone())
+    torch.save(res, os.path.join(out, "ext%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_ubernce_coclr_queues_world2(tmp_path):
+    world, B, K = 2, 4, 32
+    port = 29900 + (os.getpid() % 90)
+    mp.spawn(_worker_ext, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(os.path.join(str(tmp_path), "ext%d.pt" % i)) for i in range(world)]
+    # UberNCE (pretrain.py:211-227): labels of ALL ranks enter the label queue in rank-major order on every rank
+    assert torch.equal(r[0]["u_queue_label"], r[1]["u_queue_label"]) and r[0]["u_ptr"] == r[1]["u_ptr"] == world * B
+    assert torch.equal(r[0]["u_queue_label"][:world * B], torch.cat([r[0]["u_label"], r[1]["u_label"]]))
+    old = torch.full((K,), -1, dtype=torch.long)
+    old[:16] = torch.arange(16) % 5
+    for i in range(world):        # the mask uses the label queue as it was BEFORE this step's enqueue (pretrain.py:271)
+        want = torch.cat([torch.ones(B, 1, dtype=torch.bool), r[i]["u_label"][:, None] == old[None, :]], 1)
+        assert torch.equal(r[i]["u_mask"], want)
+    # CoCLR (pretrain.py:321-341): video ids and second-view keys of all ranks, rank-major, identical replicas
+    for key in ("c_queue_vname", "c_queue_second", "c_queue"):
+        assert torch.equal(r[0][key], r[1][key]), key
+    assert r[0]["c_ptr"] == r[1]["c_ptr"] == world * B
+    assert torch.equal(r[0]["c_queue_vname"][:world * B], torch.cat([r[0]["c_vname"], r[1]["c_vname"]]))
+    kf = torch.cat([_fake_encode(r[i]["c_f2"]) for i in range(world)])
+    assert torch.allclose(r[0]["c_queue_second"][:, :world * B], kf.T, atol=1e-6)
+    k = torch.cat([_fake_encode(r[i]["c_x2"]) for i in range(world)])
+    assert torch.allclose(r[0]["c_queue"][:, :world * B], k.T, atol=1e-6)
+    for i in range(world):        # same-source positives + topk=3 mined positives + the self column
+        m = r[i]["c_mask"]
+        src = r[i]["c_vname"][:, None] == (torch.arange(K) % 7)[None, :]
+        assert bool(m[:, 0].all()) and bool((m[:, 1:] | ~src).all())
+        assert torch.equal(m[:, 1:].sum(1), src.sum(1) + 3)
