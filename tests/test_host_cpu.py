@@ -48,10 +48,6 @@ def test_state_dict_keys_match_reference_surface():
     for k in ("queue_second", "queue_vname", "queue_label", "sampler.0.Conv_1a.conv1.weight", "sampler.4.bias"):
         assert k in c.state_dict(), k
     assert c.queue_is_full is False
-    if os.path.isdir("/root/reference/model"):
-        sys.path.insert(0, "/root/reference")
-        import importlib
-        ref = importlib.import_module("model.pretrain") if False else None  # name clash with our package: compare via oracle aliases instead
 
 
 def test_select_backbone_contract():
@@ -230,8 +226,14 @@ def test_space_to_depth_stem_is_the_same_convolution(stem):
 def test_cli_accepts_every_reference_flag():
     """Drop-in command line: every option of the reference's main_nce.py / main_coclr.py parses here, with the same
     default for the options that shape the hot path."""
-    import main_nce
-    import main_coclr
+    import importlib.util
+
+    def load(name):     # this repository's script by path (the reference has files of the same name)
+        spec = importlib.util.spec_from_file_location("coclr_b200_cli_" + name, os.path.join(ROOT, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    main_nce, main_coclr = load("main_nce"), load("main_coclr")
 
     def ref_flags(path):
         out = {}
@@ -263,9 +265,15 @@ def test_training_losses_are_the_reference_formulas():
     imported: tensorboardX / lmdb are absent): multi_nce_loss (main_coclr.py:343-346) and the UberNCE loss lines
     (main_nce.py:321-322) against main_coclr.multi_nce_loss / main_nce.multi_label_nce_loss, bit-for-bit."""
     import ast
+    import importlib.util
     import torch.nn.functional as F
-    import main_nce
-    import main_coclr
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location("coclr_b200_cli2_" + name, os.path.join(ROOT, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    main_nce, main_coclr = load("main_nce"), load("main_coclr")
     src = open("/root/reference/main_coclr.py").read()
     fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "multi_nce_loss"][0]
     ns = {"torch": torch, "F": F}
