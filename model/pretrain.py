@@ -53,6 +53,13 @@ class InfoNCE(nn.Module):
         self._side_stream = None
         self._peer_clips = {}     # clip shape -> moco.PeerClips, or False when symmetric memory is unavailable
 
+    @property
+    def module(self):
+        """The reference's scripts reach the model through its DistributedDataParallel wrapper (`model.module.sampler`,
+        `model.module.queue_is_full`, main_coclr.py:363,403).  There is no wrapper here (the flat gradient is all-reduced
+        in FlatAdam.step), so `.module` is the model itself and those call sites keep working."""
+        return self
+
     # -- fused input transform -----------------------------------------------------------------------
     def set_input_transform(self, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
         """Fold the reference's GPU-side `tr` (main_nce.py:207-209,299-302: T.Normalize(mean, std, channel=1) ->

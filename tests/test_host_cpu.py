@@ -48,6 +48,9 @@ def test_state_dict_keys_match_reference_surface():
     for k in ("queue_second", "queue_vname", "queue_label", "sampler.0.Conv_1a.conv1.weight", "sampler.4.bias"):
         assert k in c.state_dict(), k
     assert c.queue_is_full is False
+    # call sites written against the DDP-wrapped reference model keep working (main_coclr.py:363,403)
+    assert c.module is c and c.module.queue_is_full is False and c.module.sampler is c.sampler
+    assert not any(k.startswith("module.") for k in c.state_dict())
 
 
 def test_select_backbone_contract():
