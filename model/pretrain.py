@@ -90,6 +90,14 @@ class InfoNCE(nn.Module):
         assert block.shape[1] == 2                                                    # pretrain.py:148
         return block[:, 0], block[:, 1]
 
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        """Checkpoints written by the reference carry the DistributedDataParallel prefix (`module.encoder_q...`,
+        main_nce.py:172,271-279; the published pretrained files do): accepted as is."""
+        if any(k.startswith("module.") for k in state_dict):
+            state_dict = type(state_dict)((k[len("module."):] if k.startswith("module.") else k, v)
+                                          for k, v in state_dict.items())
+        return super().load_state_dict(state_dict, *args, **kwargs)
+
     # -- queue pointer mirror ---------------------------------------------------------------------
     def _load_from_state_dict(self, *args, **kwargs):
         self._ptr_host = None  # re-read the loaded pointer lazily

@@ -51,6 +51,13 @@ def test_state_dict_keys_match_reference_surface():
     # call sites written against the DDP-wrapped reference model keep working (main_coclr.py:363,403)
     assert c.module is c and c.module.queue_is_full is False and c.module.sampler is c.sampler
     assert not any(k.startswith("module.") for k in c.state_dict())
+    # a checkpoint saved from the reference's DDP-wrapped model ('module.' prefix, main_nce.py:271-279) loads as is
+    ddp_style = {"module." + k: v.clone() for k, v in m.state_dict().items()}
+    ddp_style["module.queue_ptr"] = torch.tensor([24])
+    m2 = InfoNCE("s3d", 128, 128)
+    m2.load_state_dict(ddp_style, strict=True)
+    assert int(m2.queue_ptr) == 24 and m2._ptr() == 24
+    assert torch.equal(m2.encoder_q[0].Conv_2c.conv1.weight, m.encoder_q[0].Conv_2c.conv1.weight)
 
 
 def test_select_backbone_contract():
