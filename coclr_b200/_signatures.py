@@ -11,6 +11,8 @@ LG = C.c_long
 EXPORTS = {
     "coclr_conv_igemm": (I, [P, I, P]),
     "coclr_conv_packed_bytes": (C.c_size_t, [I, I, C.POINTER(I), C.POINTER(I)]),
+    "coclr_conv_tma_plan": (I, [P, C.POINTER(I)]),
+    "coclr_set_conv_tma": (None, [I]),
     "coclr_conv_wgrad": (I, [P, P]),
     "coclr_pack_weights": (I, [P, P]),
     "coclr_affine_split": (I, [P, I, P]),

@@ -216,3 +216,53 @@ COCLR_DEVINL void split2(float v, uint16_t& hi, uint16_t& lo) {
 }
 
 }  // namespace coclr
+
+// ---------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor): tiled 5-D loads / stores / add-reductions through a CUtensorMap that lives in the
+// kernel's parameter space (const __grid_constant__); out-of-bounds box elements are zero-filled on load and
+// clipped on store, which is what implements convolution padding and ragged tile edges here.
+// ---------------------------------------------------------------------------------------------
+namespace coclr {
+COCLR_DEVINL void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+COCLR_DEVINL void tma_load_5d(uint32_t smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3,
+                              int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, "
+      "%6}], [%7];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+      : "memory");
+}
+COCLR_DEVINL void tma_store_5d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+COCLR_DEVINL void tma_reduce_add_5d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(tmap)),
+      "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+COCLR_DEVINL void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the shared-memory source of all but the newest kPending committed bulk groups may be overwritten
+template <int kPending>
+COCLR_DEVINL void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+template <int kPending>
+COCLR_DEVINL void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
+}
+COCLR_DEVINL void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+COCLR_DEVINL float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+}  // namespace coclr

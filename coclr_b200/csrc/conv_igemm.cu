@@ -19,6 +19,7 @@
 //    BatchNorm needs.
 #include "common.cuh"
 #include "coclr_b200.h"
+#include "conv_tma.h"
 
 namespace coclr {
 
@@ -797,6 +798,9 @@ extern "C" int coclr_conv_igemm(const coclr_conv_t* p, int num_sms, coclr_stream
   if (num_sms <= 0) return COCLR_E_ARG;
   if ((long long)p->B * p->src.T * p->src.H * p->src.W >= (1ll << 31)) return COCLR_E_ARG;  // 32-bit pixel indices
   cudaStream_t s = (cudaStream_t)stream;
+  // TMA-staged kernel first (conv_tma.cu); shapes it does not cover run on the cp.async gather kernel below
+  const int rc = coclr::conv_tma_try(*p, num_sms, s);
+  if (rc <= 0) return rc;
   return p->npass > 1 ? launch_conv<3>(*p, num_sms, s) : launch_conv<1>(*p, num_sms, s);
 }
 

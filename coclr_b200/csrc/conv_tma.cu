@@ -1,0 +1,764 @@
+// TMA-staged implicit-GEMM convolution on tcgen05 tensor cores (sm_100a): forward and data-gradient of the
+// stride-1 (1,k,k) / (k,1,1) / 1x1x1 convolutions and of the temporally strided (k,1,1) stem conv of the
+// reference's backbones (backbone/s3dg.py:11-13 BasicConv3d, :39-42 STConv3d conv1 / conv2; cuDNN dgrad behind
+// loss.backward(), main_nce.py:330).  Same C ABI as conv_igemm.cu (coclr_conv_igemm dispatches here first); what
+// changes is how the operands travel:
+//
+//  * the A operand (channels-last 16-bit hi / lo activation planes) is described by a 5-D CUtensorMap
+//    [channels, W, H, T, B] (or [channels, H*W, parity, T/2, B] for the temporal kernels).  One elected thread
+//    issues cp.async.bulk.tensor loads of a HALO SLAB -- the 128-pixel output tile plus the rows the other taps
+//    of the reuse dimension need -- into 128B-swizzled shared memory; convolution padding and ragged tile edges
+//    are the TMA unit's out-of-bounds zero fill.  No thread computes an address.
+//  * the taps along the reuse dimension (dy of a (1,3,3) conv, dt of a (k,1,1) conv) are served from the SAME
+//    slab: their A descriptors differ by a whole number of 8-row swizzle atoms (tile rows are a multiple of 8
+//    pixels wide), so every slab byte fetched from L2 feeds up to kh (kt) x 12 tensor-core instructions;
+//  * weights: the pre-swizzled hi / lo tile images of coclr_pack_weights, either streamed through a ring of
+//    bulk copies or -- for narrow layers whose whole image fits -- loaded ONCE per CTA and kept resident;
+//  * the epilogue drains TMEM into a swizzled staging row block, accumulates the BatchNorm statistics from it,
+//    and writes it with ONE cp.async.bulk.tensor store (or add-reduction, for gradient accumulation) per
+//    32 rows x 32 channels: edge clipping, channel slices of concat buffers and the strided frame order of the
+//    transposed stem conv are properties of the output tensor map, not code.
+//
+// Warp roles (224 threads): 0-3 epilogue (TMEM lane quadrant = warp), 4 A loader, 5 weight loader + TMEM owner,
+// 6 MMA issuer.
+#include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "coclr_b200.h"
+#include "conv_tma.h"
+
+namespace coclr {
+
+static constexpr int kTmaThreads = 7 * 32;
+static constexpr int kTmaMaxASlots = 4;
+static constexpr int kTmaMaxBSlots = 4;
+static constexpr uint32_t kStageBytes = 4096;  // 32 rows x 32 fp32 columns per epilogue warp and buffer
+
+struct TmaTile {
+  int idx[4];
+  int n_tile;
+};
+COCLR_DEVINL TmaTile tma_decode(const TmaPlan& L, int tile) {
+  TmaTile t;
+  t.n_tile = tile % L.n_tiles_n;
+  int m = tile / L.n_tiles_n;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    t.idx[d] = m % L.ntiles[d];
+    m /= L.ntiles[d];
+  }
+  t.idx[3] = m;
+  return t;
+}
+
+template <int kNPass>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+    conv_tma_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                    const __grid_constant__ CUtensorMap map_out, const __grid_constant__ TmaArgs P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr bool kLo = kNPass > 1;
+  constexpr uint32_t kPlanes = kLo ? 2u : 1u;
+  const TmaPlan& L = P.plan;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + L.off_b;
+  const uint32_t stage_base = smem_base + L.off_stage;
+  float* unscale_tab = reinterpret_cast<float*>(smem + L.off_misc);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L.off_bars);
+  uint64_t* a_empty = a_full + kTmaMaxASlots;
+  uint64_t* b_full = a_empty + kTmaMaxASlots;
+  uint64_t* b_empty = b_full + kTmaMaxBSlots;
+  uint64_t* t_full = b_empty + kTmaMaxBSlots;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTmaMaxASlots; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < kTmaMaxBSlots; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&t_full[a], 1);
+      mbar_init(&t_empty[a], 4);
+    }
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 256; i += kTmaThreads)
+    unscale_tab[i] = 1.f;  // per tile the epilogue reads n_tile*BN + c; filled below when there is a table
+  if (warp == 5) tmem_alloc<512>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 4) {
+    // ===================== A loader: one TMA box (hi) + one (lo) per slab =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&map_hi);
+      if (kLo) tma_prefetch_desc(&map_lo);
+      uint32_t slot = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < L.total_tiles; tile += gridDim.x) {
+        const TmaTile t = tma_decode(L, tile);
+        const int ty0 = L.sel_dim >= 0 ? t.idx[L.sel_dim] : 0;
+        const int ty1 = L.sel_dim >= 0 ? ty0 + 1 : L.n_types;
+        for (int cc = 0; cc < L.nc; ++cc) {
+          for (int ty = ty0; ty < ty1; ++ty) {
+            const TmaSlabType& S = L.type[ty];
+            mbar_wait(&a_empty[slot], phase ^ 1u);
+            mbar_arrive_expect_tx(&a_full[slot], kPlanes * (uint32_t)L.slab_bytes);
+            const int c0 = cc * L.a_c0_step;
+            const int c1 = t.idx[0] * L.a_mul[0] + S.d[0];
+            const int c2 = t.idx[1] * L.a_mul[1] + S.d[1];
+            const int c3 = t.idx[2] * L.a_mul[2] + S.d[2];
+            const int c4 = t.idx[3] * L.a_mul[3] + S.d[3];
+            const uint32_t dst = a_base + slot * (uint32_t)L.a_slot_bytes;
+            tma_load_5d(dst, &map_hi, &a_full[slot], c0, c1, c2, c3, c4);
+            if (kLo) tma_load_5d(dst + (uint32_t)L.plane_stride, &map_lo, &a_full[slot], c0, c1, c2, c3, c4);
+            if (++slot == (uint32_t)L.a_slots) { slot = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== weight loader (bulk copies of pre-swizzled tile images) =====================
+    if (lane == 0) {
+      const uint32_t tile_bytes = kPlanes * (uint32_t)L.BN * 128u;          // what one K chunk needs in smem
+      const size_t img_stride = (size_t)2u * (size_t)L.BN * 128u;            // packed image: hi and lo of every chunk
+      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(P.wpk);
+      if (L.b_resident) {
+        // the whole [nkc] image of the (single) N tile, once
+        mbar_arrive_expect_tx(&b_full[0], (uint32_t)L.nkc * tile_bytes);
+        for (int kc = 0; kc < L.nkc; ++kc)
+          bulk_g2s(smem + L.off_b + (size_t)kc * tile_bytes, wbase + (size_t)kc * img_stride, tile_bytes, &b_full[0]);
+      } else {
+        uint32_t slot = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < L.total_tiles; tile += gridDim.x) {
+          const TmaTile t = tma_decode(L, tile);
+          const int ty0 = L.sel_dim >= 0 ? t.idx[L.sel_dim] : 0;
+          const int ty1 = L.sel_dim >= 0 ? ty0 + 1 : L.n_types;
+          for (int cc = 0; cc < L.nc; ++cc) {
+            for (int ty = ty0; ty < ty1; ++ty) {
+              const TmaSlabType& S = L.type[ty];
+              for (int j = 0; j < S.nshift; ++j) {
+                const int kc = S.tap[j] * L.nc + cc;
+                mbar_wait(&b_empty[slot], phase ^ 1u);
+                mbar_arrive_expect_tx(&b_full[slot], tile_bytes);
+                bulk_g2s(smem + L.off_b + (size_t)slot * tile_bytes,
+                         wbase + ((size_t)t.n_tile * L.nkc + kc) * img_stride, tile_bytes, &b_full[slot]);
+                if (++slot == (uint32_t)L.b_slots) { slot = 0; phase ^= 1u; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(P.a_bf16 ? 1u : 0u, P.b_bf16 ? 1u : 0u, 0u, 0u, 128u, (uint32_t)L.BN);
+    const uint32_t tile_bytes = kPlanes * (uint32_t)L.BN * 128u;
+    const uint32_t b_lo_off = (uint32_t)L.BN * 128u;
+    uint32_t aslot = 0, aphase = 0, bslot = 0, bphase = 0, it = 0;
+    if (L.b_resident) {
+      mbar_wait_spin(&b_full[0], 0);
+      tc_fence_after();
+    }
+    for (int tile = blockIdx.x; tile < L.total_tiles; tile += gridDim.x, ++it) {
+      const TmaTile t = tma_decode(L, tile);
+      const int ty0 = L.sel_dim >= 0 ? t.idx[L.sel_dim] : 0;
+      const int ty1 = L.sel_dim >= 0 ? ty0 + 1 : L.n_types;
+      const uint32_t acc = it & 1u;
+      mbar_wait_spin(&t_empty[acc], ((it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * 256u;
+      uint32_t started = 0;
+      for (int cc = 0; cc < L.nc; ++cc) {
+        for (int ty = ty0; ty < ty1; ++ty) {
+          const TmaSlabType& S = L.type[ty];
+          mbar_wait_spin(&a_full[aslot], aphase);
+          tc_fence_after();
+          const uint32_t sa0 = a_base + aslot * (uint32_t)L.a_slot_bytes;
+          for (int j = 0; j < S.nshift; ++j) {
+            uint32_t sb;
+            if (L.b_resident) {
+              sb = b_base + (uint32_t)(S.tap[j] * L.nc + cc) * tile_bytes;
+            } else {
+              mbar_wait_spin(&b_full[bslot], bphase);
+              tc_fence_after();
+              sb = b_base + bslot * tile_bytes;
+            }
+            if (lane == 0) {
+              const uint32_t sa = sa0 + (uint32_t)j * (uint32_t)L.shift_bytes;
+              const uint64_t a_hi = make_smem_desc(sa, 16, 1024);
+              const uint64_t b_hi = make_smem_desc(sb, 16, 1024);
+              if constexpr (kLo) {
+                const uint64_t a_lo = make_smem_desc(sa + (uint32_t)L.plane_stride, 16, 1024);
+                const uint64_t b_lo = make_smem_desc(sb + b_lo_off, 16, 1024);
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, (started | k) != 0);
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+              } else {
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (started | k) != 0);
+              }
+              if (!L.b_resident) umma_commit(&b_empty[bslot]);
+            }
+            started = 1u;
+            __syncwarp();
+            if (!L.b_resident) {
+              if (++bslot == (uint32_t)L.b_slots) { bslot = 0; bphase ^= 1u; }
+            }
+          }
+          if (lane == 0) umma_commit(&a_empty[aslot]);   // the slab may be overwritten once these MMAs have read it
+          __syncwarp();
+          if (++aslot == (uint32_t)L.a_slots) { aslot = 0; aphase ^= 1u; }
+        }
+      }
+      if (lane == 0) umma_commit(&t_full[acc]);
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue (warps 0-3) =====================
+    const bool want_stats = P.stats_sum != nullptr;
+    if (P.wunscale != nullptr && L.n_tiles_n == 1) {
+      for (int i = threadIdx.x; i < L.BN; i += 128) unscale_tab[i] = __ldg(P.wunscale + i);
+    }
+    named_bar_sync(1, 128);
+    const uint32_t my_stage = stage_base + (uint32_t)warp * (uint32_t)L.stage_bufs * kStageBytes;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+    // box-relative position of this lane's row (rows are in box order, dim 1 fastest)
+    int ri[4];
+    {
+      int r = warp * 32 + lane;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        ri[d] = r % L.obox[d];
+        r /= L.obox[d];
+      }
+      ri[3] = r;
+    }
+    uint32_t it = 0, nstore = 0;
+    for (int tile = blockIdx.x; tile < L.total_tiles; tile += gridDim.x, ++it) {
+      const TmaTile t = tma_decode(L, tile);
+      const uint32_t acc = it & 1u;
+      bool valid = true;
+      int oc[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int o = t.idx[d] * L.o_mul[d];
+        valid = valid && (o + ri[d] < L.oext[d]);
+        oc[d] = o + L.sub[warp][d];
+      }
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      if (P.wunscale != nullptr && L.n_tiles_n > 1) {
+        named_bar_sync(1, 128);   // previous tile's readers are done with the table
+        for (int i = threadIdx.x; i < L.BN; i += 128) unscale_tab[i] = __ldg(P.wunscale + t.n_tile * L.BN + i);
+        named_bar_sync(1, 128);
+      }
+      mbar_wait(&t_full[acc], (it >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int kq = 0; kq < 8; ++kq) {
+        const int c0 = kq * 32;
+        const int col0 = t.n_tile * L.BN + c0;
+        if (c0 < L.BN && col0 < L.N) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 256u + (uint32_t)c0, v);
+          tmem_ld_wait();
+          const uint32_t buf = my_stage + (L.stage_bufs == 2 ? (nstore & 1u) : 0u) * kStageBytes;
+          if (lane == 0) {
+            // the bulk store that last read this buffer must have finished reading it
+            if (L.stage_bufs == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+          }
+          __syncwarp();
+          const uint32_t rowaddr = buf + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 u = *reinterpret_cast<const float4*>(unscale_tab + c0 + 4 * q);
+            st_shared_v4(rowaddr + (((uint32_t)q ^ ((uint32_t)lane & 7u)) << 4),
+                         __uint_as_float(v[4 * q + 0]) * u.x, __uint_as_float(v[4 * q + 1]) * u.y,
+                         __uint_as_float(v[4 * q + 2]) * u.z, __uint_as_float(v[4 * q + 3]) * u.w);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (P.accumulate) tma_reduce_add_5d(&map_out, buf, col0, oc[0], oc[1], oc[2], oc[3]);
+            else tma_store_5d(&map_out, buf, col0, oc[0], oc[1], oc[2], oc[3]);
+            bulk_commit_group();
+          }
+          ++nstore;
+          if (want_stats) {
+            // lane c sums column c over the warp's valid rows, reading the swizzled block back (conflict-free)
+            float a = 0.f, b = 0.f;
+            const uint32_t cchunk = (uint32_t)lane >> 2, cword = ((uint32_t)lane & 3u) << 2;
+#pragma unroll 8
+            for (uint32_t r = 0; r < 32; ++r) {
+              if ((vmask >> r) & 1u) {
+                const float x = ld_shared_f32(buf + r * 128u + ((cchunk ^ (r & 7u)) << 4) + cword);
+                a += x;
+                b = fmaf(x, x, b);
+              }
+            }
+            s1[kq] += a;
+            s2[kq] += b;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (want_stats && L.n_tiles_n > 1) {
+#pragma unroll
+        for (int kq = 0; kq < 8; ++kq) {
+          const int col = t.n_tile * L.BN + kq * 32 + lane;
+          if (kq * 32 < L.BN && col < L.N) {
+            atomicAdd(&P.stats_sum[col], (double)s1[kq]);
+            atomicAdd(&P.stats_sq[col], (double)s2[kq]);
+          }
+          s1[kq] = s2[kq] = 0.f;
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_group_read<0>();
+    __syncwarp();
+    if (want_stats && L.n_tiles_n == 1) {
+      // combine the four warps' column sums in shared memory (the staging blocks are free now), one fp64 atomic per
+      // channel and CTA
+      float* tab = reinterpret_cast<float*>(smem + L.off_stage);   // [4 warps][2][256]
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int kq = 0; kq < 8; ++kq) {
+        tab[(warp * 2 + 0) * 256 + kq * 32 + lane] = s1[kq];
+        tab[(warp * 2 + 1) * 256 + kq * 32 + lane] = s2[kq];
+      }
+      named_bar_sync(1, 128);
+      for (int c = threadIdx.x; c < L.N; c += 128) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          a += (double)tab[(w * 2 + 0) * 256 + c];
+          b += (double)tab[(w * 2 + 1) * 256 + c];
+        }
+        atomicAdd(&P.stats_sum[c], a);
+        atomicAdd(&P.stats_sq[c], b);
+      }
+    }
+    if (lane == 0) bulk_wait_group<0>();   // all global writes of this thread's bulk stores are complete
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    __syncwarp();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: applicability, tile plan, tensor maps
+// ------------------------------------------------------------------------------------------------
+struct MapSpec {
+  void* base[2];
+  uint64_t dims[5];
+  uint64_t strides[4];   // bytes, dims 1..4
+  uint32_t box[5];
+  int elem_bytes;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static bool encode_map(CUtensorMap* m, const MapSpec& s, int which) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], estr[5];
+  for (int i = 0; i < 5; ++i) {
+    dims[i] = s.dims[i];
+    box[i] = s.box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i < 4; ++i) strides[i] = s.strides[i];
+  const CUtensorMapDataType dt = s.elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
+  CUresult r = fn(m, dt, 5, s.base[which], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (getenv("COCLR_TMA_DEBUG")) fprintf(stderr, "coclr: cuTensorMapEncodeTiled failed (%d)\n", (int)r);
+    return false;
+  }
+  return true;
+}
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static int pymod(int a, int b) { return ((a % b) + b) % b; }
+
+// Fills the plan and the two map specs; returns false when this launch shape stays on the cp.async kernel.
+bool conv_tma_plan(const coclr_conv_t& P, TmaPlan& L, MapSpec& A, MapSpec& O) {
+  const coclr_geom_t& g = P.g;
+  const coclr_src_t& S = P.src;
+  memset(&L, 0, sizeof(L));
+  if (P.npass != 1 && P.npass != 3) return false;
+  const int taps = g.kt * g.kh * g.kw;
+  // K = tap * C + channel is cut into 64-wide chunks: chunks must not straddle taps (single-tap convs may end with a
+  // partial chunk: the TMA unit zero-fills channels past C and the packed weights are zero past Kreal)
+  if (S.C % 8 != 0 || (taps > 1 && S.C % 64 != 0)) return false;
+  if (P.BN % 32 != 0 || P.BN > 256 || P.n_tiles < 1) return false;
+  if (P.Kreal != g.kt * g.kh * g.kw * S.C) return false;
+  if (g.sh != 1 || g.sw != 1) return false;
+  const int planes = P.npass > 1 ? 2 : 1;
+  const long ld2 = (long)S.ld * 2;
+  L.BN = P.BN;
+  L.N = P.N;
+  L.n_tiles_n = P.n_tiles;
+  L.nc = (S.C + 63) / 64;
+  L.nkc = taps * L.nc;
+  L.sel_dim = -1;
+  L.a_c0_step = 64;
+  A.elem_bytes = 2;
+  A.base[0] = (void*)((const uint16_t*)S.hi + S.coff);
+  A.base[1] = S.lo ? (void*)((const uint16_t*)S.lo + S.coff) : nullptr;
+  O.elem_bytes = 4;
+  O.base[0] = (void*)(P.dst + P.dst_coff);
+  O.base[1] = nullptr;
+  const long old4 = (long)P.dst_ld * 4;
+  int box[4] = {1, 1, 1, 1};     // tile extent per logical dim
+  for (int d = 0; d < 4; ++d) L.ntiles[d] = 1;
+  const bool tr = g.transposed != 0;
+
+  if (g.kt == 1 && g.kh == 1 && g.kw == 1) {
+    // ---- 1x1x1: a plain GEMM over the flattened pixels ----
+    if (g.st != 1) return false;
+    if (S.T != P.Td || S.H != P.Hd || S.W != P.Wd) return false;
+    const long M = (long)P.B * P.Td * P.Hd * P.Wd;
+    if (M >= (1l << 31)) return false;
+    box[0] = 128;
+    L.ntiles[0] = ceil_div((int)M, 128);
+    A.dims[0] = S.C; A.dims[1] = M; A.dims[2] = A.dims[3] = A.dims[4] = 1;
+    A.strides[0] = ld2; A.strides[1] = A.strides[2] = A.strides[3] = (uint64_t)ld2 * M;
+    A.box[0] = 64; A.box[1] = 128; A.box[2] = A.box[3] = A.box[4] = 1;
+    O.dims[0] = P.N; O.dims[1] = M; O.dims[2] = O.dims[3] = O.dims[4] = 1;
+    O.strides[0] = old4; O.strides[1] = O.strides[2] = O.strides[3] = (uint64_t)old4 * M;
+    L.oext[0] = (int)M; L.oext[1] = L.oext[2] = L.oext[3] = 1;
+    L.n_types = 1;
+    L.type[0].nshift = 1;
+    L.type[0].tap[0] = 0;
+    L.slab_bytes = 128 * 128;
+    L.shift_bytes = 0;
+  } else if (g.kt == 1) {
+    // ---- (1, kh, kw), stride 1: dy taps share one slab, one slab type per dx ----
+    if (g.st != 1 || g.kw > 4 || g.kh > 8) return false;
+    if (S.T != P.Td || S.H != P.Hd || S.W != P.Wd) return false;
+    int nw, nh;
+    if (S.W % 16 == 0) { nw = 16; nh = 8; }
+    else if (S.W % 8 == 0) { nw = 8; nh = 16; }
+    else return false;
+    if (S.H < nh) return false;
+    box[0] = nw; box[1] = nh;
+    L.ntiles[0] = ceil_div(S.W, nw); L.ntiles[1] = ceil_div(S.H, nh); L.ntiles[2] = S.T; L.ntiles[3] = P.B;
+    A.dims[0] = S.C; A.dims[1] = S.W; A.dims[2] = S.H; A.dims[3] = S.T; A.dims[4] = P.B;
+    A.strides[0] = ld2; A.strides[1] = ld2 * S.W; A.strides[2] = ld2 * S.W * S.H; A.strides[3] = ld2 * S.W * S.H * S.T;
+    A.box[0] = 64; A.box[1] = nw; A.box[2] = nh + g.kh - 1; A.box[3] = 1; A.box[4] = 1;
+    O.dims[0] = P.N; O.dims[1] = P.Wd; O.dims[2] = P.Hd; O.dims[3] = P.Td; O.dims[4] = P.B;
+    O.strides[0] = old4; O.strides[1] = old4 * P.Wd; O.strides[2] = old4 * P.Wd * P.Hd;
+    O.strides[3] = old4 * P.Wd * P.Hd * P.Td;
+    L.oext[0] = P.Wd; L.oext[1] = P.Hd; L.oext[2] = P.Td; L.oext[3] = P.B;
+    L.n_types = g.kw;
+    for (int xa = 0; xa < g.kw; ++xa) {
+      TmaSlabType& t = L.type[xa];
+      t.d[0] = tr ? g.pw - xa : xa - g.pw;
+      t.d[1] = tr ? g.ph - (g.kh - 1) : -g.ph;
+      t.nshift = g.kh;
+      for (int j = 0; j < g.kh; ++j) {
+        const int ya = tr ? g.kh - 1 - j : j;
+        t.tap[j] = ya * g.kw + xa;
+      }
+    }
+    L.slab_bytes = nw * (nh + g.kh - 1) * 128;
+    L.shift_bytes = nw * 128;
+  } else if (g.kh == 1 && g.kw == 1) {
+    // ---- (kt, 1, 1): pixels of a frame are one flat dimension, dt taps share one slab ----
+    if (g.kt > 8) return false;
+    if (S.H != P.Hd || S.W != P.Wd) return false;
+    const int HW = S.H * S.W;
+    int npx, nt;
+    const int t_tiles_over = (g.st == 1) ? P.Td : (tr ? P.Td / 2 : P.Td);
+    if (HW % 16 == 0 && t_tiles_over >= 8) { npx = 16; nt = 8; }
+    else if (HW % 32 == 0 && t_tiles_over >= 4) { npx = 32; nt = 4; }
+    else return false;
+    box[0] = npx; box[2] = nt;
+    const long oHW = (long)P.Hd * P.Wd;
+    if (g.st == 1) {
+      if (S.T != P.Td) return false;
+      L.ntiles[0] = ceil_div(HW, npx); L.ntiles[2] = ceil_div(P.Td, nt); L.ntiles[3] = P.B;
+      A.dims[0] = S.C; A.dims[1] = HW; A.dims[2] = 1; A.dims[3] = S.T; A.dims[4] = P.B;
+      A.strides[0] = ld2; A.strides[1] = ld2 * HW; A.strides[2] = ld2 * HW; A.strides[3] = ld2 * HW * S.T;
+      A.box[0] = 64; A.box[1] = npx; A.box[2] = 1; A.box[3] = nt + g.kt - 1; A.box[4] = 1;
+      O.dims[0] = P.N; O.dims[1] = oHW; O.dims[2] = 1; O.dims[3] = P.Td; O.dims[4] = P.B;
+      O.strides[0] = old4; O.strides[1] = old4 * oHW; O.strides[2] = old4 * oHW; O.strides[3] = old4 * oHW * P.Td;
+      L.oext[0] = (int)oHW; L.oext[1] = 1; L.oext[2] = P.Td; L.oext[3] = P.B;
+      L.n_types = 1;
+      TmaSlabType& t = L.type[0];
+      t.d[2] = tr ? g.pt - (g.kt - 1) : -g.pt;
+      t.nshift = g.kt;
+      for (int j = 0; j < g.kt; ++j) t.tap[j] = tr ? g.kt - 1 - j : j;
+      L.slab_bytes = npx * (nt + g.kt - 1) * 128;
+    } else if (g.st == 2 && !tr) {
+      // forward, temporal stride 2: input frame 2*t' - pt + dt = 2*(t' + sh) + par; one slab type per frame parity
+      if (S.T % 2 != 0 || (S.T + 2 * g.pt - g.kt) / 2 + 1 != P.Td) return false;
+      L.ntiles[0] = ceil_div(HW, npx); L.ntiles[2] = ceil_div(P.Td, nt); L.ntiles[3] = P.B;
+      int maxshift = 0;
+      L.n_types = 2;
+      for (int par = 0; par < 2; ++par) {
+        TmaSlabType& t = L.type[par];
+        t.nshift = 0;
+        int sh_min = 0;
+        for (int dt = 0; dt < g.kt; ++dt) {
+          if (pymod(dt - g.pt, 2) != par) continue;
+          const int sh = (dt - g.pt - par) / 2;   // exact
+          if (t.nshift == 0) sh_min = sh;
+          t.tap[t.nshift++] = dt;
+        }
+        if (t.nshift == 0) return false;
+        t.d[1] = par;
+        t.d[2] = sh_min;
+        maxshift = t.nshift > maxshift ? t.nshift : maxshift;
+      }
+      A.dims[0] = S.C; A.dims[1] = HW; A.dims[2] = 2; A.dims[3] = S.T / 2; A.dims[4] = P.B;
+      A.strides[0] = ld2; A.strides[1] = ld2 * HW; A.strides[2] = ld2 * HW * 2; A.strides[3] = ld2 * HW * S.T;
+      A.box[0] = 64; A.box[1] = npx; A.box[2] = 1; A.box[3] = nt + maxshift - 1; A.box[4] = 1;
+      O.dims[0] = P.N; O.dims[1] = oHW; O.dims[2] = 1; O.dims[3] = P.Td; O.dims[4] = P.B;
+      O.strides[0] = old4; O.strides[1] = old4 * oHW; O.strides[2] = old4 * oHW; O.strides[3] = old4 * oHW * P.Td;
+      L.oext[0] = (int)oHW; L.oext[1] = 1; L.oext[2] = P.Td; L.oext[3] = P.B;
+      L.slab_bytes = npx * (nt + maxshift - 1) * 128;
+    } else if (g.st == 2 && tr) {
+      // data gradient of the temporally strided conv: output frame t = 2*th + par receives dY[th + sh] * W[dt] with
+      // dt = par + pt - 2*sh; the frame parity of a tile selects its slab type
+      if (P.Td % 2 != 0 || (P.Td + 2 * g.pt - g.kt) / 2 + 1 != S.T) return false;
+      const int TH = P.Td / 2;
+      L.ntiles[0] = ceil_div(HW, npx); L.ntiles[1] = 2; L.ntiles[2] = ceil_div(TH, nt); L.ntiles[3] = P.B;
+      L.sel_dim = 1;
+      L.n_types = 2;
+      int maxshift = 0;
+      for (int par = 0; par < 2; ++par) {
+        TmaSlabType& t = L.type[par];
+        t.nshift = 0;
+        int sh_min = 0;
+        for (int dt = g.kt - 1; dt >= 0; --dt) {    // descending dt = ascending sh
+          if (pymod(par + g.pt - dt, 2) != 0) continue;
+          const int sh = (par + g.pt - dt) / 2;     // may be negative: C division of an even number is exact
+          if (t.nshift == 0) sh_min = sh;
+          t.tap[t.nshift++] = dt;
+        }
+        if (t.nshift == 0) return false;
+        t.d[2] = sh_min;
+        maxshift = t.nshift > maxshift ? t.nshift : maxshift;
+      }
+      A.dims[0] = S.C; A.dims[1] = HW; A.dims[2] = 1; A.dims[3] = S.T; A.dims[4] = P.B;
+      A.strides[0] = ld2; A.strides[1] = ld2 * HW; A.strides[2] = ld2 * HW; A.strides[3] = ld2 * HW * S.T;
+      A.box[0] = 64; A.box[1] = npx; A.box[2] = 1; A.box[3] = nt + maxshift - 1; A.box[4] = 1;
+      O.dims[0] = P.N; O.dims[1] = oHW; O.dims[2] = 2; O.dims[3] = TH; O.dims[4] = P.B;
+      O.strides[0] = old4; O.strides[1] = old4 * oHW; O.strides[2] = old4 * oHW * 2; O.strides[3] = old4 * oHW * P.Td;
+      L.oext[0] = (int)oHW; L.oext[1] = 2; L.oext[2] = TH; L.oext[3] = P.B;
+      L.slab_bytes = npx * (nt + maxshift - 1) * 128;
+    } else {
+      return false;
+    }
+    L.shift_bytes = npx * 128;
+  } else {
+    return false;
+  }
+  if (L.slab_bytes / 128 > 256 * 4) return false;
+  for (int d = 0; d < 4; ++d) {
+    L.obox[d] = box[d];
+    L.a_mul[d] = box[d];
+    L.o_mul[d] = box[d];
+  }
+  if (L.sel_dim >= 0) {          // parity dimension: tile index = output parity coordinate, no A coordinate
+    L.a_mul[L.sel_dim] = 0;
+    L.o_mul[L.sel_dim] = 1;
+  }
+  if (g.st == 2 && !tr && g.kt > 1) L.a_mul[1] = 0, L.o_mul[1] = 0;   // A parity coordinate comes from the slab type
+  long mt = 1;
+  for (int d = 0; d < 4; ++d) mt *= L.ntiles[d];
+  if (mt * L.n_tiles_n >= (1l << 31)) return false;
+  L.m_tiles = (int)mt;
+  L.total_tiles = (int)(mt * L.n_tiles_n);
+  // epilogue sub-boxes: 32 consecutive tile rows form a rectangular box (all extents are powers of two)
+  int sb[4], rem = 32;
+  for (int d = 0; d < 4; ++d) {
+    sb[d] = box[d] < rem ? box[d] : rem;
+    rem /= sb[d];
+  }
+  if (rem != 1) return false;
+  O.box[0] = 32;
+  for (int d = 0; d < 4; ++d) O.box[1 + d] = sb[d];
+  for (int w = 0; w < 4; ++w) {
+    int r = 32 * w;
+    for (int d = 0; d < 4; ++d) {
+      L.sub[w][d] = r % box[d];
+      r /= box[d];
+    }
+  }
+  // alignment / limits of the tensor maps
+  for (int i = 0; i < 2; ++i)
+    if (A.base[i] && ((uintptr_t)A.base[i] & 15)) return false;
+  if (planes == 2 && !A.base[1]) return false;
+  if (((uintptr_t)O.base[0] & 15) || (old4 % 16) != 0 || (ld2 % 16) != 0) return false;
+  for (int d = 0; d < 5; ++d)
+    if (A.box[d] > 256 || O.box[d] > 256 || A.dims[d] == 0 || O.dims[d] == 0) return false;
+  // ---- shared memory ----
+  L.plane_stride = (L.slab_bytes + 1023) & ~1023;
+  L.a_slot_bytes = planes * L.plane_stride;
+  L.b_tile_bytes = planes * L.BN * 128;
+  const int budget = 227 * 1024 - 1024 /*alignment slack*/ - 1024 /*unscale table*/ - 256 /*barriers*/;
+  const int stage1 = 4 * (int)kStageBytes, stage2 = 8 * (int)kStageBytes;
+  int steps_per_tile = 0;
+  for (int ty = 0; ty < L.n_types; ++ty) steps_per_tile += L.type[ty].nshift;
+  steps_per_tile *= L.nc;
+  const long tiles_per_cta = ((long)L.total_tiles + 147) / 148;
+  L.b_resident = 0;
+  const long resident_bytes = (long)L.nkc * L.b_tile_bytes;
+  if (L.n_tiles_n == 1 && tiles_per_cta >= 2 && resident_bytes + 2l * L.a_slot_bytes + stage1 <= budget) {
+    L.b_resident = 1;
+    L.b_slots = 0;
+    long left = budget - resident_bytes;
+    L.stage_bufs = (left - stage2 >= 2l * L.a_slot_bytes) ? 2 : 1;
+    left -= L.stage_bufs == 2 ? stage2 : stage1;
+    L.a_slots = (int)(left / L.a_slot_bytes);
+    if (L.a_slots > kTmaMaxASlots) L.a_slots = kTmaMaxASlots;
+    L.off_b = (uint32_t)(L.a_slots * L.a_slot_bytes);
+    L.off_stage = L.off_b + (uint32_t)resident_bytes;
+  } else {
+    L.stage_bufs = 2;
+    long left = budget - stage2;
+    if (left < 2l * L.a_slot_bytes + 2l * L.b_tile_bytes) {
+      L.stage_bufs = 1;
+      left = budget - stage1;
+      if (left < 2l * L.a_slot_bytes + 2l * L.b_tile_bytes) return false;
+    }
+    L.a_slots = 2;
+    L.b_slots = 2;
+    left -= 2l * L.a_slot_bytes + 2l * L.b_tile_bytes;
+    // spend what is left on the ring whose entries are consumed faster first (weights: one per 64-deep K step)
+    while (true) {
+      if (L.b_slots < kTmaMaxBSlots && L.b_slots <= L.a_slots * 2 && left >= L.b_tile_bytes) {
+        ++L.b_slots; left -= L.b_tile_bytes;
+      } else if (L.a_slots < kTmaMaxASlots && left >= L.a_slot_bytes) {
+        ++L.a_slots; left -= L.a_slot_bytes;
+      } else if (L.b_slots < kTmaMaxBSlots && left >= L.b_tile_bytes) {
+        ++L.b_slots; left -= L.b_tile_bytes;
+      } else break;
+    }
+    L.off_b = (uint32_t)(L.a_slots * L.a_slot_bytes);
+    L.off_stage = L.off_b + (uint32_t)(L.b_slots * L.b_tile_bytes);
+  }
+  L.off_stage = (L.off_stage + 1023u) & ~1023u;
+  L.off_misc = L.off_stage + (uint32_t)(L.stage_bufs == 2 ? stage2 : stage1);
+  L.off_bars = L.off_misc + 1024u;
+  L.total = L.off_bars + 256u + 1024u;
+  if (L.total > 227u * 1024u) return false;
+  if (L.stage_bufs == 1 && P.stats_sum != nullptr) {
+    // the end-of-kernel statistics table (4 warps x 2 x 256 floats = 8 KB) lives in the staging area
+    if (4 * (int)kStageBytes < 8192) return false;
+  }
+  (void)steps_per_tile;
+  return true;
+}
+
+}  // namespace coclr
+
+using namespace coclr;
+
+static int g_tma_enabled = -1;
+
+static bool tma_enabled() {
+  if (g_tma_enabled < 0) {
+    const char* e = getenv("COCLR_TMA");
+    g_tma_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_tma_enabled == 1;
+}
+
+extern "C" void coclr_set_conv_tma(int enabled) { g_tma_enabled = enabled ? 1 : 0; }
+
+// Debug / test entry: the tile plan this launch shape would get (no GPU needed). Returns 1 when the TMA kernel
+// applies and fills info[] = {a_slots, b_slots, b_resident, stage_bufs, total smem, total tiles, slab bytes, n_types}.
+extern "C" int coclr_conv_tma_plan(const coclr_conv_t* p, int* info) {
+  if (!p) return 0;
+  TmaPlan L;
+  MapSpec A, O;
+  if (!conv_tma_plan(*p, L, A, O)) return 0;
+  if (info) {
+    info[0] = L.a_slots; info[1] = L.b_slots; info[2] = L.b_resident; info[3] = L.stage_bufs;
+    info[4] = (int)L.total; info[5] = L.total_tiles; info[6] = L.slab_bytes; info[7] = L.n_types;
+  }
+  return 1;
+}
+
+// Returns COCLR_OK when the launch was issued, 1 when this shape is not handled here (caller falls through to the
+// cp.async kernel), a negative COCLR_E_* on a launch error.
+int coclr::conv_tma_try(const coclr_conv_t& P, int num_sms, cudaStream_t stream) {
+  if (!tma_enabled()) return 1;
+  TmaArgs args;
+  MapSpec A, O;
+  if (!conv_tma_plan(P, args.plan, A, O)) return 1;
+  CUtensorMap m_hi, m_lo, m_out;
+  if (!encode_map(&m_hi, A, 0)) return 1;
+  if (P.npass > 1) {
+    if (!encode_map(&m_lo, A, 1)) return 1;
+  } else {
+    m_lo = m_hi;
+  }
+  if (!encode_map(&m_out, O, 0)) return 1;
+  args.wpk = P.wpk;
+  args.wunscale = P.wunscale;
+  args.stats_sum = P.stats_sum;
+  args.stats_sq = P.stats_sq;
+  args.accumulate = P.accumulate;
+  args.a_bf16 = P.a_bf16;
+  args.b_bf16 = P.b_bf16;
+  const TmaPlan& L = args.plan;
+  const int grid = L.total_tiles < num_sms ? L.total_tiles : num_sms;
+  cudaError_t e;
+  if (P.npass > 1) {
+    e = cudaFuncSetAttribute(conv_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    if (e != cudaSuccess) return COCLR_E_LAUNCH;
+    conv_tma_kernel<3><<<grid, kTmaThreads, L.total, stream>>>(m_hi, m_lo, m_out, args);
+  } else {
+    e = cudaFuncSetAttribute(conv_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    if (e != cudaSuccess) return COCLR_E_LAUNCH;
+    conv_tma_kernel<1><<<grid, kTmaThreads, L.total, stream>>>(m_hi, m_lo, m_out, args);
+  }
+  return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
+}

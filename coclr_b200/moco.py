@@ -66,12 +66,18 @@ class _EncodeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, enc, x, training):
         plan = enc._engine_for(x.device).forward(x, training=training, with_backward=True, norm=enc.input_norm)
-        ctx.enc, ctx.plan = enc, plan
+        # the plan (activation buffers + captured graphs) is shared by every pass of this shape: remember which pass
+        # filled it, so that a backward whose activations were overwritten by a later forward fails loudly
+        plan.generation = getattr(plan, "generation", 0) + 1
+        ctx.enc, ctx.plan, ctx.generation = enc, plan, plan.generation
         return plan.q.clone()
 
     @staticmethod
     def backward(ctx, dq):
         enc = ctx.enc
+        if ctx.plan.generation != ctx.generation:
+            raise L.CoclrError("backward of an encoder pass whose saved activations were overwritten by a later forward "
+                               "of the same shape (one outstanding training forward per encoder and input shape)")
         enc._prepare_grads()
         enc._engine.backward(ctx.plan, dq.contiguous())
         return None, None, None, None

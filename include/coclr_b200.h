@@ -73,6 +73,15 @@ typedef struct {
 } coclr_conv_t;
 int coclr_conv_igemm(const coclr_conv_t* p, int num_sms, coclr_stream_t stream);
 size_t coclr_conv_packed_bytes(int N, int Kreal, int* BN_out, int* n_tiles_out);
+/* coclr_conv_igemm runs stride-1 (1,k,k) / (k,1,1) / 1x1x1 shapes (and the temporally strided (k,1,1) stem conv) whose
+ * K chunks do not straddle taps on the TMA-staged kernel (csrc/conv_tma.cu: cp.async.bulk.tensor halo slabs shared by
+ * the taps of one dimension, resident or streamed weight tiles, bulk-tensor store / add-reduce epilogue) and everything
+ * else on the cp.async gather kernel.  coclr_conv_tma_plan reports (without a GPU) whether a launch takes the TMA
+ * kernel: returns 1 and fills info[8] = {A slots, B slots, weights resident, staging buffers, shared-memory bytes,
+ * tiles, slab bytes per plane, slab types}, else 0.  coclr_set_conv_tma(0) forces the gather kernel (tests, A/B
+ * timing; also COCLR_TMA=0 in the environment). */
+int coclr_conv_tma_plan(const coclr_conv_t* p, int* info);
+void coclr_set_conv_tma(int enabled);
 
 /* ---- weight-gradient -----------------------------------------------------------------------
  * replaces cuDNN wgrad.  dW[n, c, tap] += sum_m dY[m, n] * A[m, (tap, c)] into the PyTorch weight

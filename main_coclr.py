@@ -74,18 +74,48 @@ class SyntheticTwoStream:
         return self.args.steps_per_epoch
 
 
-def load_two_checkpoints(model, paths):
-    """First path -> encoder_q / encoder_k, second -> the frozen sampler (reference main_coclr.py:250-302)."""
+def _strip_module(k):
+    return k[len('module.'):] if k.startswith('module.') else k
+
+
+def two_checkpoint_state(paths):
+    """State dict of the reference's two-checkpoint initialisation (main_coclr.py:250-302):
+      * second path = the ORACLE: only its encoder_q.* weights, renamed sampler.* (never trained here);
+      * first path  = the network to train: only its encoder_q.* weights, copied into BOTH encoder_q.* and encoder_k.*
+        (its own encoder_k.* EMA weights, its sampler.* -- present from co-training cycle 2 on -- and every queue
+        buffer are dropped);
+      * merged as {**first, **second}; the queues are always re-filled."""
+    second = {}
     if os.path.isfile(paths[1]):
-        sd = torch.load(paths[1], map_location='cpu')['state_dict']
-        new = {k.replace('encoder_q.', 'sampler.'): v for k, v in sd.items()
-               if k.startswith('encoder_q.') or k.startswith('module.encoder_q.')}
-        new = {k.replace('module.', ''): v for k, v in new.items()}
-        print(model.load_state_dict(new, strict=False))
+        ckpt = torch.load(paths[1], map_location='cpu')
+        for k, v in ckpt['state_dict'].items():
+            k = _strip_module(k)
+            if 'encoder_q.' in k and 'queue' not in k:
+                second[k.replace('encoder_q.', 'sampler.')] = v
+        print("=> Use Oracle checkpoint '%s' (epoch %s)" % (paths[1], ckpt.get('epoch')))
+    else:
+        print("=> NO Oracle checkpoint found at '%s', use random init" % paths[1])
+    first = {}
     if os.path.isfile(paths[0]):
-        sd = torch.load(paths[0], map_location='cpu')['state_dict']
-        new = {k.replace('module.', ''): v for k, v in sd.items() if 'queue' not in k}
-        print(model.load_state_dict(new, strict=False))
+        ckpt = torch.load(paths[0], map_location='cpu')
+        for k, v in ckpt['state_dict'].items():
+            k = _strip_module(k)
+            if 'encoder_q.' in k and 'queue' not in k:
+                first[k] = v
+                first[k.replace('encoder_q.', 'encoder_k.')] = v
+        print("=> Use Training checkpoint '%s' (epoch %s)" % (paths[0], ckpt.get('epoch')))
+    else:
+        print("=> NO Training checkpoint found at '%s', use random init" % paths[0])
+    state = {**first, **second}
+    state.pop('queue_label', None)
+    return state
+
+
+def load_two_checkpoints(model, paths):
+    """One non-strict load of two_checkpoint_state() (the reference uses neq_load_customized, main_coclr.py:302)."""
+    res = model.load_state_dict(two_checkpoint_state(paths), strict=False)
+    print('missing keys: %d, unexpected keys: %d' % (len(res.missing_keys), len(res.unexpected_keys)))
+    return res
 
 
 def train_one_epoch(loader, model, optimizer, epoch, args):
@@ -129,22 +159,47 @@ def main_worker(args):
     random.seed(args.seed)
     model = CoCLR(args.net, args.moco_dim, args.moco_k, args.moco_m, args.moco_t, topk=args.topk,
                   reverse=args.reverse, precision=args.precision)
-    if args.pretrain2 != ['random', 'random']:
-        load_two_checkpoints(model, args.pretrain2)
     model = model.to(device)
     optimizer = moco.FlatAdam(model.encoder_q, lr=args.lr, weight_decay=args.wd)
     args.iteration = 1
+    best_acc = 0.0
+    if args.resume:                                               # restart training (reference main_coclr.py:230-248)
+        if os.path.isfile(args.resume):
+            ckpt = torch.load(args.resume, map_location='cpu')
+            args.start_epoch = ckpt['epoch'] + 1
+            args.iteration = ckpt.get('iteration', 1)
+            best_acc = ckpt.get('best_acc', 0.0)
+            try:
+                model.load_state_dict(ckpt['state_dict'])
+            except RuntimeError:
+                print('[WARNING] Non-Equal load for resuming training!')
+                print(model.load_state_dict(ckpt['state_dict'], strict=False))
+            print("=> load resumed checkpoint '%s' (epoch %d)" % (args.resume, ckpt['epoch']))
+            if not base.load_optimizer_state(optimizer, ckpt.get('optimizer'), model.encoder_q, device):
+                print('[WARNING] Not loading optimizer states')
+        else:
+            print("[Warning] no checkpoint found at '%s', use random init" % args.resume)
+    elif args.pretrain2 != ['random', 'random']:
+        load_two_checkpoints(model, args.pretrain2)
+    if args.test:
+        return model
     if not args.synthetic:
         raise NotImplementedError("the 2-stream LMDB datasets are outside the accelerated hot path; use --synthetic")
     loader = SyntheticTwoStream(args, device)
     model_path = base.set_path(args)
     for epoch in range(args.start_epoch, args.epochs):
+        np.random.seed(epoch)                                      # reference main_coclr.py:314-315: the 90 % self-mask
+        random.seed(epoch)                                         # draws restart per epoch (reproducible across resume)
         base.adjust_learning_rate(optimizer, epoch, args)
         loss, acc = train_one_epoch(loader, model, optimizer, epoch, args)
         if args.rank == 0 and ((epoch % args.save_freq == 0) or (epoch == args.epochs - 1)):
-            base.save_checkpoint({'epoch': epoch, 'state_dict': model.state_dict(), 'best_acc': acc,
+            is_best = acc > best_acc
+            best_acc = max(acc, best_acc)
+            base.save_checkpoint({'epoch': epoch, 'state_dict': model.state_dict(), 'best_acc': best_acc,
                                   'optimizer': optimizer.state_dict(), 'iteration': args.iteration},
-                                 False, gap=args.save_freq, filename=os.path.join(model_path, 'epoch%d.pth.tar' % epoch))
+                                 is_best, gap=args.save_freq,
+                                 filename=os.path.join(model_path, 'epoch%d.pth.tar' % epoch),
+                                 keep_all='k400' in args.dataset)
     print('Training from ep %d to ep %d finished' % (args.start_epoch, args.epochs))
     if args.distributed:
         dist.destroy_process_group()

@@ -13,8 +13,10 @@ GPU; --local_rank, --local-rank and the LOCAL_RANK env variable are all accepted
 
 What differs from the reference loop (main_nce.py:286-353), by design:
   * no DistributedDataParallel wrapper: the encoder's backward writes one flat gradient buffer that
-    FlatAdam all-reduces (mean) in one NCCL call; BN buffers / queue are replica-identical by construction, so DDP's
-    per-step buffer broadcast (SURVEY.md C6) has nothing to do;
+    FlatAdam all-reduces (mean) in one NCCL call; weights and queue are replica-identical by construction, so DDP's
+    per-step buffer broadcast has nothing to do for them.  BatchNorm RUNNING statistics are per-rank
+    (no SyncBN, as in the reference) and are not read in train mode; rank 0's copy is the one that is saved, which is
+    what the reference's rank-0 broadcast + rank-0 save amounts to;
   * top-k accuracy and loss are accumulated on the device and read back every --print_freq steps
     (the reference forces three .item() syncs per step, main_nce.py:325-327).
 """
@@ -205,6 +207,44 @@ def train_one_epoch(loader, model, optimizer, epoch, args):
     return s[0] / n, s[1] / n
 
 
+def load_optimizer_state(optimizer, sd, encoder, device):
+    """Restore FlatAdam from a checkpoint's 'optimizer' entry: either FlatAdam's own flat state or a torch.optim.Adam
+    state_dict as the reference writes it (main_nce.py:190-200,276: one param group per named_parameter of the WHOLE
+    model in named_parameters() order; only the encoder_q tensors carry state).  Returns False when nothing usable was
+    found (the moments then restart from zero, which the caller reports)."""
+    if not isinstance(sd, dict):
+        return False
+    if 'exp_avg' in sd:
+        optimizer.load_state_dict({k: (v.to(device) if torch.is_tensor(v) else v) for k, v in sd.items()})
+        return True
+    state, groups = sd.get('state'), sd.get('param_groups')
+    if not isinstance(state, dict) or not groups:
+        return False
+    named = list(encoder.named_parameters())      # encoder_q's tensors are the first entries of the reference's list
+    ids = [i for g in groups for i in g['params']]
+    if len(ids) < len(named):
+        return False
+    st = optimizer._state()
+    steps = []
+    for (name, p), i in zip(named, ids):
+        ent = state.get(i)
+        if ent is None:
+            continue
+        if tuple(ent['exp_avg'].shape) != tuple(p.shape):
+            print('[WARNING] optimizer state of parameter %d does not have the shape of %s' % (i, name))
+            return False
+        off, n, _ = st.offsets[name]
+        optimizer.exp_avg[off:off + n].copy_(ent['exp_avg'].reshape(-1).to(device))
+        optimizer.exp_avg_sq[off:off + n].copy_(ent['exp_avg_sq'].reshape(-1).to(device))
+        steps.append(int(ent['step']))
+    if not steps:
+        return False
+    optimizer.step_count = max(steps)
+    g0 = groups[0]
+    optimizer.param_groups[0].update({k: g0[k] for k in ('lr', 'betas', 'eps', 'weight_decay') if k in g0})
+    return True
+
+
 def main_worker(args):
     setup_distributed(args)
     device = torch.device('cuda', args.gpu)
@@ -227,9 +267,8 @@ def main_worker(args):
             args.start_epoch = ckpt['epoch'] + 1              # reference main_nce.py:218
             args.iteration = ckpt.get('iteration', 1)
             best_acc = ckpt.get('best_acc', 0.0)
-            if not args.reset_lr and isinstance(ckpt.get('optimizer'), dict) and 'exp_avg' in ckpt['optimizer']:
-                optimizer.load_state_dict({k: (v.to(device) if torch.is_tensor(v) else v)
-                                           for k, v in ckpt['optimizer'].items()})
+            if not args.reset_lr and not load_optimizer_state(optimizer, ckpt.get('optimizer'), model.encoder_q, device):
+                print('[WARNING] Not loading optimizer states')      # reference main_nce.py:231-232
     if args.test:
         return model
     loader = get_data(args, device)

@@ -300,3 +300,89 @@ def test_training_losses_are_the_reference_formulas():
         env = {"F": F, "output": logits, "target": mask}
         exec(uber[0], env)
         assert torch.equal(main_nce.multi_label_nce_loss(logits, mask), env["loss"].mean())
+
+
+def _load_cli(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("coclr_b200_cli_" + name, os.path.join(ROOT, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_two_checkpoint_init_follows_reference(tmp_path):
+    """main_coclr.py --pretrain A B (reference main_coclr.py:250-302): ONLY encoder_q.* of A goes into encoder_q AND
+    encoder_k (A's own EMA weights, A's sampler.* -- present when A is itself a CoCLR checkpoint, i.e. from co-training
+    cycle 2 on -- and all queues are dropped); ONLY encoder_q.* of B becomes the sampler."""
+    main_coclr = _load_cli("main_coclr")
+    from model.pretrain import CoCLR, InfoNCE
+    torch.manual_seed(0)
+    a = CoCLR("s3d", 128, 128, topk=5)       # first checkpoint: a CoCLR-shaped state (has sampler.* and queue_second)
+    b = InfoNCE("s3d", 128, 128)             # second checkpoint: the oracle
+    with torch.no_grad():
+        for i, m in enumerate((a.encoder_q, a.encoder_k, a.sampler, b.encoder_q, b.encoder_k)):
+            m[4].bias.fill_(float(i + 1))    # q_A=1, k_A=2, sampler_A=3 (stale), q_B=4, k_B=5
+    pa, pb = str(tmp_path / "a.pth.tar"), str(tmp_path / "b.pth.tar")
+    torch.save({"epoch": 7, "state_dict": {"module." + k: v for k, v in a.state_dict().items()}}, pa)   # DDP-style keys
+    torch.save({"epoch": 9, "state_dict": b.state_dict()}, pb)
+    state = main_coclr.two_checkpoint_state([pa, pb])
+    assert not any("queue" in k for k in state)
+    assert float(state["encoder_q.4.bias"][0]) == 1.0 and float(state["encoder_k.4.bias"][0]) == 1.0
+    assert float(state["sampler.4.bias"][0]) == 4.0          # the oracle's encoder_q, NOT A's stale sampler (3)
+    model = CoCLR("s3d", 128, 128, topk=5)
+    q0 = model.queue.clone()
+    res = main_coclr.load_two_checkpoints(model, [pa, pb])
+    assert not res.unexpected_keys
+    assert all("queue" in k for k in res.missing_keys)
+    assert float(model.encoder_q[4].bias[0]) == 1.0 and float(model.encoder_k[4].bias[0]) == 1.0
+    assert float(model.sampler[4].bias[0]) == 4.0
+    assert torch.equal(model.encoder_k[0].Conv_2c.conv1.weight, a.encoder_q[0].Conv_2c.conv1.weight)
+    assert torch.equal(model.queue, q0)                      # queues are always re-filled
+    # the reference's own merge, restated from its source text, gives the same key -> source mapping
+    ref_src = open("/root/reference/main_coclr.py").read() if os.path.exists("/root/reference/main_coclr.py") else ""
+    if ref_src:
+        assert "state_dict = {**first_dict, **second_dict}" in ref_src
+        assert "k = k.replace('encoder_q.', 'encoder_k.')" in ref_src and "k.replace('encoder_q.', 'sampler.')" in ref_src
+
+
+def test_reference_adam_state_converts_to_flat(tmp_path):
+    """A checkpoint written by the reference carries a torch.optim.Adam state_dict with one param group per
+    named_parameter of the whole model (main_nce.py:190-200,276); resuming from it must restore the moments and the step
+    count of encoder_q instead of silently restarting them.  Uses the dry-run store (no CUDA)."""
+    main_nce = _load_cli("main_nce")
+    from coclr_b200 import lib as L, moco
+    from model.pretrain import InfoNCE
+    torch.manual_seed(0)
+    model = InfoNCE("s3d", 128, 128)
+    params = [{"params": p} for _, p in model.named_parameters()]       # reference main_nce.py:190-198
+    ref_opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-5)
+    for p in model.encoder_q.parameters():
+        p.grad = torch.randn_like(p) * 1e-3
+    ref_opt.step()
+    ref_opt.step()
+    sd = ref_opt.state_dict()
+    L.DRY_RUN = True
+    try:
+        from coclr_b200.engine import Graph, ParamStore
+
+        class _Enc:      # the two things load_optimizer_state needs from an encoder: named_parameters() and .store
+            def __init__(self, enc):
+                bb = enc[0]
+                g = Graph(bb._stages, bb.input_channel, head_dim=enc.dim, feature_size=enc.feature_size, bb_prefix="0.")
+                self.store, self._enc = ParamStore(g, "cpu"), enc
+
+            def named_parameters(self):
+                return self._enc.named_parameters()
+        enc = _Enc(model.encoder_q)
+        opt = moco.FlatAdam(enc, lr=1e-3, weight_decay=1e-5)
+        assert main_nce.load_optimizer_state(opt, sd, enc, "cpu")
+        assert opt.step_count == 2
+        names = [n for n, _ in model.encoder_q.named_parameters()]
+        for i in (0, 17, len(names) - 1):
+            off, n, _ = enc.store.offsets[names[i]]
+            assert torch.equal(opt.exp_avg[off:off + n], sd["state"][i]["exp_avg"].reshape(-1))
+            assert torch.equal(opt.exp_avg_sq[off:off + n], sd["state"][i]["exp_avg_sq"].reshape(-1))
+        assert not main_nce.load_optimizer_state(opt, None, enc, "cpu")
+        assert not main_nce.load_optimizer_state(opt, {"state": {}, "param_groups": []}, enc, "cpu")
+    finally:
+        L.DRY_RUN = False
