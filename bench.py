@@ -39,6 +39,12 @@ def parse():
                     help="backbone: s3d = BASELINE.json configs 1-4 (headline), r50 = config 5 (ResNet2d3d-50)")
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--seq_len", type=int, default=CFG["seq_len"])
+    ap.add_argument("--moco-k", type=int, default=CFG["K"], help="queue length: 2048 = config 2 (headline), 16384 = config 3")
+    ap.add_argument("--model", default="infonce", choices=["infonce", "coclr"],
+                    help="infonce = configs 1-3,5; coclr = config 4 (2-stream co-training step: q fwd+bwd, k fwd, frozen "
+                         "sampler fwd, top-k mined positives)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the first step")
+    ap.add_argument("--no-stock-gpu", action="store_true", help="skip the stock-PyTorch-on-this-GPU baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel time table of one step to stderr")
@@ -131,12 +137,12 @@ def reference_arm(args):
         return
     batch, sample_T = 1, 8
     steps = max(1, min(args.steps, 3))
-    val, med = cpu_oracle_clips_per_s(batch, sample_T, CFG["img"], CFG["K"], steps, 1, args.net)
-    line = {"impl": "reference", "metric": "clips/sec %s InfoNCE (32x128^2, K=2048)" % NET_NAME[args.net], "value": val, "unit": "clips/s",
+    val, med = cpu_oracle_clips_per_s(batch, sample_T, CFG["img"], args.moco_k, steps, 1, args.net)
+    line = {"impl": "reference", "metric": "clips/sec %s InfoNCE (32x128^2, K=%d)" % (NET_NAME[args.net], args.moco_k), "value": val, "unit": "clips/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": med * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "InfoNCE %s moco-k=2048 128^2 full train step (fwd+bwd+Adam), bounded sample: "
-                                   "%d clip pair(s) of %d frames per step, scaled to 32-frame clips" % (NET_NAME[args.net], batch, sample_T),
+            "config": {"workload": "InfoNCE %s moco-k=%d 128^2 full train step (fwd+bwd+Adam), bounded sample: "
+                                   "%d clip pair(s) of %d frames per step, scaled to 32-frame clips" % (NET_NAME[args.net], args.moco_k, batch, sample_T),
                        "batch_per_step": batch, "sample_seq_len": sample_T},
             "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": "oracle port of the reference (torch CPU fp32), %d timed steps of %d pair(s) of "
@@ -144,6 +150,127 @@ def reference_arm(args):
                                        "is pure Python and cannot travel to the GPU box" % (steps, batch, sample_T, sample_T)},
             "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
+
+
+# ------------------------------------------------------------------------------------------------
+# parity of the benched configuration: the FIRST training step of the run against the oracle (checker only; nothing
+# of oracle/ is on the timed path).  Works for any world size: rank 0 simulates the W-rank world (shuffle-BN
+# permutation, per-rank BatchNorm, global enqueue) in float64 from the gathered inputs and the pre-step state.
+# ------------------------------------------------------------------------------------------------
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def parity_first_step(model, run_step, block, world, rank, dev):
+    import torch.distributed as dist
+    from oracle import coclr_oracle as O
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    seed = 4242
+    torch.manual_seed(seed)              # rank 0 draws the shuffle-BN permutation from the CPU RNG (pretrain.py:112)
+    logits, loss = run_step(block)
+    torch.cuda.synchronize()
+    if world > 1:
+        blocks_all = torch.empty((world,) + tuple(block.shape), dtype=block.dtype, device=dev)
+        dist.all_gather_into_tensor(blocks_all, block.contiguous())
+        logits_all = torch.empty((world,) + tuple(logits.shape), dtype=logits.dtype, device=dev)
+        dist.all_gather_into_tensor(logits_all, logits.detach().contiguous())
+    else:
+        blocks_all, logits_all = block[None], logits.detach()[None]
+    out = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            sdd = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd0.items()}
+            for k in O.param_keys(sdd, "encoder_q."):
+                sdd[k].requires_grad_(True)
+            torch.manual_seed(seed)
+            idx = torch.randperm(block.shape[0] * world).to(dev)
+            ref_logits, labels = O.infonce_forward(sdd, [blocks_all[r].double() for r in range(world)], idx,
+                                                   keep_graph=False)
+            e_logits = max(_rel(logits_all[r], ref_logits[r]) for r in range(world))
+            ref_loss = float(O.infonce_loss(ref_logits[0], labels.to(dev)))
+            e_queue = _rel(model.queue, sdd["queue"])
+            out = {"oracle": "oracle/coclr_oracle.py in float64 on the same GPU, simulated %d-rank world" % world,
+                   "step": "first training step of this run (B=%d per rank)" % block.shape[0],
+                   "logits_rel_err": e_logits, "loss": float(loss), "loss_oracle": ref_loss,
+                   "loss_rel_err": abs(float(loss) - ref_loss) / max(1.0, abs(ref_loss)),
+                   "queue_rel_err": e_queue, "queue_ptr": [int(model.queue_ptr), int(sdd["queue_ptr"])],
+                   "tolerance": 1e-3, "seconds": None}
+            out["ok"] = bool(e_logits < 1e-3 and out["loss_rel_err"] < 1e-3 and e_queue < 1e-3 and
+                             out["queue_ptr"][0] == out["queue_ptr"][1])
+            del sdd, ref_logits
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+        torch.cuda.synchronize()
+        out["seconds"] = round(time.perf_counter() - t0, 2)
+    del blocks_all, logits_all, sd0
+    torch.cuda.empty_cache()
+    return out
+
+
+def replicas_identical(model, world, dev):
+    """Bit-exact comparison of every rank's parameters and queue (an order-independent 64-bit checksum of the raw bits)."""
+    import torch.distributed as dist
+    cs = torch.stack([model.encoder_q.store.flat.view(torch.int32).to(torch.int64).sum(),
+                      model.encoder_k.store.flat.view(torch.int32).to(torch.int64).sum(),
+                      model.queue.contiguous().view(torch.int32).to(torch.int64).sum()])
+    if world == 1:
+        return True
+    allc = torch.empty(world, 3, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allc, cs)
+    return bool((allc == allc[0:1]).all())
+
+
+# ------------------------------------------------------------------------------------------------
+# the same training step in stock PyTorch ops (the oracle's restatement of the reference, cuDNN / cuBLAS) on THIS GPU:
+# what the unmodified reference would reach on a B200 -- "the Blackwell kernels to beat" (SURVEY.md 2a / 8d).
+# fp32-strict is the arithmetic the 1e-3 parity bar needs; TF32 is PyTorch's default (misses the bar by ~40x).
+# ------------------------------------------------------------------------------------------------
+def stock_gpu_baseline(batch, seq_len, img, K, net, dev, steps=3):
+    from oracle import coclr_oracle as O
+    out = {"impl": "oracle ops in stock PyTorch %s / cuDNN %s on the same GPU" % (torch.__version__, torch.backends.cudnn.version()),
+           "batch": batch, "steps": steps, "unit": "clips/s"}
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        for mode in ("fp32", "tf32"):
+            torch.backends.cudnn.allow_tf32 = mode == "tf32"
+            torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
+            torch.backends.cudnn.benchmark = True
+            sd = {k: v.to(dev) for k, v in O.synth_state(O.infonce_shapes(128, K, network=net), seed=0).items()}
+            qkeys = O.param_keys(sd, "encoder_q.")
+            for k in qkeys:
+                sd[k].requires_grad_(True)
+            state = {}
+            block = torch.randn(batch, 2, 3, seq_len, img, img, device=dev)
+
+            def step():
+                idx = torch.randperm(batch).to(dev)
+                logits, labels = O.infonce_forward(sd, [block], idx)
+                loss = O.infonce_loss(logits[0], labels.to(dev))
+                grads = torch.autograd.grad(loss, [sd[k] for k in qkeys])
+                O.adam_step({k: sd[k] for k in qkeys}, dict(zip(qkeys, grads)), state)
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = {"ms_per_step": ms, "value": 2.0 * batch / (ms * 1e-3)}
+            del sd, state, block
+            torch.cuda.empty_cache()
+    except Exception as ex:  # pragma: no cover
+        out["error"] = repr(ex)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = prev
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -233,26 +360,46 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    from model.pretrain import InfoNCE
+    from model.pretrain import InfoNCE, CoCLR
     from coclr_b200 import moco, lib as L
 
-    B, T, HW, K = args.batch, args.seq_len, CFG["img"], CFG["K"]
+    B, T, HW, K = args.batch, args.seq_len, CFG["img"], args.moco_k
+    coclr = args.model == "coclr"
     torch.manual_seed(0)                                   # main_nce.py:97-99
-    model = InfoNCE(args.net, CFG["dim"], K, CFG["m"], CFG["T"], precision=args.precision).to(dev).train()
+    if coclr:
+        model = CoCLR(args.net, CFG["dim"], K, CFG["m"], CFG["T"], topk=5, precision=args.precision).to(dev).train()
+        model.sampler.eval()                               # main_coclr.py:363
+        model.queue_label.fill_(1)                         # a full queue: the top-k mining and the optimizer step run (:400-406)
+        model.queue_vname.copy_(torch.arange(K, device=dev) % 997)
+    else:
+        model = InfoNCE(args.net, CFG["dim"], K, CFG["m"], CFG["T"], precision=args.precision).to(dev).train()
     opt = moco.FlatAdam(model.encoder_q, lr=1e-3, weight_decay=1e-5)
     gen = torch.Generator().manual_seed(1000 + rank)
-    host_blocks = [torch.randn(B, 2, 3, T, HW, HW, generator=gen).pin_memory() for _ in range(2)]
+    nblk = 2 if coclr else 1                               # CoCLR reads two blocks per sample (clip 1 and clip 2, RGB + flow)
+    host_blocks = [torch.randn(nblk * B, 2, 3, T, HW, HW, generator=gen).pin_memory() for _ in range(2)]
     dev_blocks = [hb.to(dev) for hb in host_blocks]       # 2 x 403 MB > 126 MB L2: inputs never L2-resident
-    loss_keep = [None]
+    vname = torch.randint(0, 997, (B,), device=dev)
+    loss_keep = [None, None]
 
     def train_step(block):
-        logits, labels = model(block)
-        loss = moco.nce_cross_entropy(logits, labels)
+        if coclr:
+            import main_coclr
+            logits, mask = model(block[:B], block[B:], vname)
+            loss = main_coclr.multi_nce_loss(logits, mask)
+        else:
+            logits, labels = model(block)
+            loss = moco.nce_cross_entropy(logits, labels)
         opt.zero_grad()
         loss.backward()
         opt.step()
-        loss_keep[0] = loss
+        loss_keep[0], loss_keep[1] = loss, logits
         return loss
+
+    # ---- parity of this configuration, before anything is timed (all ranks take part; rank 0 runs the oracle) ----
+    parity = None
+    if not args.no_parity and not coclr:
+        parity = parity_first_step(model, lambda blk: (train_step(blk), loss_keep[1], loss_keep[0])[1:], dev_blocks[0],
+                                   world, rank, dev)
 
     def barrier():
         if world > 1:
@@ -275,6 +422,7 @@ def main():
     e1.record()
     barrier()
     launches = (L.LAUNCHES - l0) // max(1, args.steps)
+    same_replicas = replicas_identical(model, world, dev)
     ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -319,6 +467,8 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": 2.0 * B * world / float(tt), "unit": "clips/s",
                "h2d_bytes_per_step": host_blocks[0].numel() * 4, "d2h_bytes_per_step": 4}
+        del stage
+        torch.cuda.empty_cache()
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -338,9 +488,10 @@ def main():
     # `ncu --set full` capture; its algorithmic bytes are one read of the fp16 hi/lo input planes + one fp32 write
     traffic, traffic_note = None, None
     try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")))["ncu_r01_fwd_conv2c.ncu-rep"]
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_full_summary.json")))["ncu_r02_tma_conv2c1_fwd.ncu-rep"]
         traffic = (cap["dram__bytes_read.sum"]["value"] + cap["dram__bytes_write.sum"]["value"]) * 1e6
-        traffic_note = ("bytes of ONE launch: Conv_2c.conv1 forward, M=524288 N=192 K=576 (profiles/r01_ncu_full_summary.json); "
+        traffic_note = ("bytes of ONE launch of the kernel as benched (TMA-staged): Conv_2c.conv1 forward, M=524288 N=192 "
+                        "K=576, from the committed `ncu --set full` capture (profiles/r02_ncu_full_summary.json); "
                         "algorithmic = 134.2e6 (input planes, read once) + 402.7e6 (fp32 output) bytes")
     except Exception:
         pass
@@ -393,21 +544,32 @@ def main():
             except Exception as ex:  # pragma: no cover
                 cpu = {"value": None, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
                        "sample": "failed: %r" % (ex,)}
-        line = {"metric": "clips/sec %s InfoNCE (32x128^2, K=2048)" % NET_NAME[args.net], "value": value, "unit": "clips/s",
+        stock = None
+        if not args.no_stock_gpu and world == 1 and not coclr:
+            stock = stock_gpu_baseline(B, T, HW, K, args.net, dev)
+        mname = "InfoNCE" if not coclr else "CoCLR 2-stream topk=5"
+        line = {"metric": "clips/sec %s %s (32x128^2, K=%d)" % (NET_NAME[args.net], mname, K), "value": value, "unit": "clips/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (fp16/bf16 hi-lo split operands, fp32 accumulate)" if args.precision == "parity" else
                          ("bf16" if args.precision == "fast" else "f32 forward / bf16 backward"),
                 "data": "synthetic",
-                "config": {"workload": "InfoNCE %s moco-k=2048 bs=%d/GPU seq_len=%d 128^2, full train step "
-                                       "(q fwd, EMA, shuffle-BN k fwd, fused logits+CE, enqueue, bwd, all-reduce, Adam)"
-                                       % (NET_NAME[args.net], B, T),
+                "config": {"workload": ("InfoNCE %s moco-k=%d bs=%d/GPU seq_len=%d 128^2, full train step "
+                                        "(q fwd, EMA, shuffle-BN k fwd, fused logits+CE, enqueue, bwd, all-reduce, Adam)"
+                                        % (NET_NAME[args.net], K, B, T)) if not coclr else
+                                       ("CoCLR %s moco-k=%d topk=5 bs=%d/GPU seq_len=%d 128^2, full co-training step with a "
+                                        "full queue (q fwd, EMA, shuffle-BN k fwd, frozen eval-BN sampler fwd on the second "
+                                        "view, fused logits, same-source + top-k mined mask, multi-positive NCE loss, "
+                                        "enqueue x2, bwd, all-reduce, Adam); 2 of the 4 clips of a sample are counted"
+                                        % (NET_NAME[args.net], K, B, T)),
                            "global_batch": B * world, "parallelism": "dp%d" % world, "precision": args.precision,
                            "l2": "two alternating 403 MB input blocks per rank (> 126 MB L2)",
                            "pairs_per_s": value / 2, "final_loss": final_loss, "host_enqueue_ms_per_step": host_ms,
-                           "algorithmic_tflops": value / 2 * GFLOP_PER_PAIR[args.net] * (T / 32.0) / 1e3},
+                           "algorithmic_tflops": value / 2 * GFLOP_PER_PAIR[args.net] * (1.25 if coclr else 1.0) * (T / 32.0) / 1e3},
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline}
+                "roofline": roofline, "parity": parity, "replicas_identical": same_replicas}
+        if stock is not None:
+            line["stock_gpu_baseline"] = stock
         if cpu is not None:
             line["cpu_baseline"] = cpu
         emit(line)

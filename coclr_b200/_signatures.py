@@ -24,7 +24,7 @@ EXPORTS = {
     "coclr_avgpool_fwd": (I, [P, P, I, I, I, P, I, I, I, P]),
     "coclr_avgpool_bwd": (I, [P, P, I, I, I, I, I, P]),
     "coclr_pack_input": (I, [P, LG, LG, I, P, P, P, P, I, LG, P, P, I, P, P, P]),
-    "coclr_pack_input_s2d": (I, [P, LG, LG, I, P, P, P, P, I, I, I, I, P, P, I, P, P, P]),
+    "coclr_pack_input_s2d": (I, [P, LG, LG, I, P, P, P, P, I, I, I, I, I, P, P, I, P, P, P]),
     "coclr_l2norm_fwd": (I, [P, P, P, P, I, I, P]),
     "coclr_l2norm_bwd": (I, [P, P, P, P, P, I, I, P]),
     "coclr_ema_update": (I, [P, P, F, F, LG, I, P]),
@@ -32,6 +32,7 @@ EXPORTS = {
     "coclr_adam_step": (I, [P, I, P]),
     "coclr_nce_logits_ce": (I, [P, P, P, F, I, I, I, P, P, P, P]),
     "coclr_nce_logits_bwd": (I, [P, P, P, F, I, I, I, P, P]),
+    "coclr_mask_topk": (I, [P, P, P, P, I, I, I, I, P, P]),
 }
 
 

@@ -195,6 +195,17 @@ COCLR_DEVINL float4 ldg_nc_f4(const float* p) {
   return r;
 }
 
+// One lane of a converged warp.  Unlike `lane == 0`, ptxas knows that code under an elect.sync predicate is executed by
+// exactly one thread, so operands of uniform-datapath instructions issued there (tcgen05.mma / .commit, cp.async.bulk.*)
+// are moved to uniform registers ONCE; under a plain lane test every such instruction is wrapped in a "waterfall" loop
+// (ELECT / 5x R2UR.BROADCAST / BRA.U.ANY, ~15 instructions and ~100 cycles per MMA) that caps the tensor pipe at the
+// issue rate of the loop instead of the rate of the MMAs.
+COCLR_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 COCLR_DEVINL void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

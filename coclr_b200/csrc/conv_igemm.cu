@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);   // warp-uniform for the compiler
 
   if (warp >= kEpiWarps && warp < kEpiWarps + kProducerWarps) {
     // ===================== A-operand producers (address generation + cp.async only) =====================
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
     }
   } else if (warp == 13) {
     // ===================== weight loader (bulk copies) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t copies = kLo ? 2u : 1u;
       const uint32_t bytes = copies * L.b_bytes;
       uint32_t stage = 0, phase = 0;
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
         if ((zmask >> kc) & 1ull) continue;
         mbar_wait_spin(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * L.stage_bytes);
           const uint32_t sb = sa + (kLo ? 2u : 1u) * L.a_bytes;
           const uint64_t a_hi = make_smem_desc(sa, 16, 1024);
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
         __syncwarp();
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
-      if (lane == 0) umma_commit(&tfull_bar[acc]);   // fires when every MMA of this tile has completed
+      if (elect_one()) umma_commit(&tfull_bar[acc]);   // fires when every MMA of this tile has completed
       __syncwarp();
     }
   } else if (warp < kEpiWarps) {
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);   // warp-uniform for the compiler
 
   if (warp >= kEpiWarps && warp < kEpiWarps + kProducerWarps) {
     const int pt = threadIdx.x - kEpiWarps * 32;
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
     for (int ch = 0; ch < nch; ++ch) {
       mbar_wait_spin(&full_bar[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t s_dy = smem_u32(smem + stage * L.stage_bytes);
         const uint32_t s_a = s_dy + (kLo ? 2u : 1u) * L.dy_bytes;
         // MN-major: LBO = stride between 64-element MN blocks (64 px * 128 B), SBO = 8-pixel group stride

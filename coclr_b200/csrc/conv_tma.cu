@@ -100,11 +100,11 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);   // warp-uniform for the compiler
 
   if (warp == 4) {
     // ===================== A loader: one TMA box (hi) + one (lo) per slab =====================
-    if (lane == 0) {
+    if (elect_one()) {
       tma_prefetch_desc(&map_hi);
       if (kLo) tma_prefetch_desc(&map_lo);
       uint32_t slot = 0, phase = 0;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
   } else if (warp == 5) {
     // ===================== weight loader (bulk copies of pre-swizzled tile images) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t tile_bytes = kPlanes * (uint32_t)L.BN * 128u;          // what one K chunk needs in smem
       const size_t img_stride = (size_t)2u * (size_t)L.BN * 128u;            // packed image: hi and lo of every chunk
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(P.wpk);
@@ -166,6 +166,13 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   } else if (warp == 6) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc(P.a_bf16 ? 1u : 0u, P.b_bf16 ? 1u : 0u, 0u, 0u, 128u, (uint32_t)L.BN);
+    // stacked mode (narrow layers): the hi rows and the lo rows of a weight tile are adjacent in shared memory, so
+    // a_hi x [b_hi; b_lo] is ONE instruction with N = 2*BN whose second half of the accumulator collects a_hi*b_lo;
+    // with a_lo x b_hi that is 2 instructions per K step instead of 3, and a third less operand traffic from shared
+    // memory -- which, not the tensor pipe, bounds M=128 x N<=128 instructions (A 4 KB + B 32*N bytes per 16-deep step
+    // against 128 B/clk).  The epilogue adds the two halves.
+    const uint32_t idesc2 = make_idesc(P.a_bf16 ? 1u : 0u, P.b_bf16 ? 1u : 0u, 0u, 0u, 128u, 2u * (uint32_t)L.BN);
+    const bool stacked = kLo && L.stacked;
     const uint32_t tile_bytes = kPlanes * (uint32_t)L.BN * 128u;
     const uint32_t b_lo_off = (uint32_t)L.BN * 128u;
     uint32_t aslot = 0, aphase = 0, bslot = 0, bphase = 0, it = 0;
@@ -197,19 +204,26 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
               tc_fence_after();
               sb = b_base + bslot * tile_bytes;
             }
-            if (lane == 0) {
+            if (elect_one()) {
               const uint32_t sa = sa0 + (uint32_t)j * (uint32_t)L.shift_bytes;
               const uint64_t a_hi = make_smem_desc(sa, 16, 1024);
               const uint64_t b_hi = make_smem_desc(sb, 16, 1024);
               if constexpr (kLo) {
                 const uint64_t a_lo = make_smem_desc(sa + (uint32_t)L.plane_stride, 16, 1024);
                 const uint64_t b_lo = make_smem_desc(sb + b_lo_off, 16, 1024);
+                if (stacked) {
+#pragma unroll
+                  for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc2, (started | k) != 0);
+#pragma unroll
+                  for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                } else {
 #pragma unroll
                 for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, (started | k) != 0);
 #pragma unroll
                 for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
 #pragma unroll
                 for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                }
               } else {
 #pragma unroll
                 for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (started | k) != 0);
@@ -222,17 +236,20 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
               if (++bslot == (uint32_t)L.b_slots) { bslot = 0; bphase ^= 1u; }
             }
           }
-          if (lane == 0) umma_commit(&a_empty[aslot]);   // the slab may be overwritten once these MMAs have read it
+          if (elect_one()) umma_commit(&a_empty[aslot]);   // the slab may be overwritten once these MMAs have read it
           __syncwarp();
           if (++aslot == (uint32_t)L.a_slots) { aslot = 0; aphase ^= 1u; }
         }
       }
-      if (lane == 0) umma_commit(&t_full[acc]);
+      if (elect_one()) umma_commit(&t_full[acc]);
       __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 0-3) =====================
     const bool want_stats = P.stats_sum != nullptr;
+    // the bulk-tensor stores of a warp are issued, committed and waited for by ONE thread (bulk async-groups are
+    // per-thread state): elected once (elect.sync is deterministic for a given member mask)
+    const bool leader = elect_one();
     if (P.wunscale != nullptr && L.n_tiles_n == 1) {
       for (int i = threadIdx.x; i < L.BN; i += 128) unscale_tab[i] = __ldg(P.wunscale + i);
     }
@@ -279,9 +296,17 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         if (c0 < L.BN && col0 < L.N) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 256u + (uint32_t)c0, v);
-          tmem_ld_wait();
+          if (kLo && L.stacked) {
+            uint32_t v2[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 256u + (uint32_t)(L.BN + c0), v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+          } else {
+            tmem_ld_wait();
+          }
           const uint32_t buf = my_stage + (L.stage_bufs == 2 ? (nstore & 1u) : 0u) * kStageBytes;
-          if (lane == 0) {
+          if (leader) {
             // the bulk store that last read this buffer must have finished reading it
             if (L.stage_bufs == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
           }
@@ -296,7 +321,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (leader) {
             if (P.accumulate) tma_reduce_add_5d(&map_out, buf, col0, oc[0], oc[1], oc[2], oc[3]);
             else tma_store_5d(&map_out, buf, col0, oc[0], oc[1], oc[2], oc[3]);
             bulk_commit_group();
@@ -321,7 +346,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (leader) mbar_arrive(&t_empty[acc]);
       if (want_stats && L.n_tiles_n > 1) {
 #pragma unroll
         for (int kq = 0; kq < 8; ++kq) {
@@ -334,7 +359,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         }
       }
     }
-    if (lane == 0) bulk_wait_group_read<0>();
+    if (leader) bulk_wait_group_read<0>();
     __syncwarp();
     if (want_stats && L.n_tiles_n == 1) {
       // combine the four warps' column sums in shared memory (the staging blocks are free now), one fp64 atomic per
@@ -358,7 +383,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         atomicAdd(&P.stats_sq[c], b);
       }
     }
-    if (lane == 0) bulk_wait_group<0>();   // all global writes of this thread's bulk stores are complete
+    if (leader) bulk_wait_group<0>();   // all global writes of this thread's bulk stores are complete
   }
 
   tc_fence_before();
@@ -424,7 +449,7 @@ static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static int pymod(int a, int b) { return ((a % b) + b) % b; }
 
 // Fills the plan and the two map specs; returns false when this launch shape stays on the cp.async kernel.
-bool conv_tma_plan(const coclr_conv_t& P, TmaPlan& L, MapSpec& A, MapSpec& O) {
+static bool conv_tma_plan_variant(const coclr_conv_t& P, int variant, TmaPlan& L, MapSpec& A, MapSpec& O) {
   const coclr_geom_t& g = P.g;
   const coclr_src_t& S = P.src;
   memset(&L, 0, sizeof(L));
@@ -432,7 +457,13 @@ bool conv_tma_plan(const coclr_conv_t& P, TmaPlan& L, MapSpec& A, MapSpec& O) {
   const int taps = g.kt * g.kh * g.kw;
   // K = tap * C + channel is cut into 64-wide chunks: chunks must not straddle taps (single-tap convs may end with a
   // partial chunk: the TMA unit zero-fills channels past C and the packed weights are zero past Kreal)
-  if (S.C % 8 != 0 || (taps > 1 && S.C % 64 != 0)) return false;
+  // window kind (space-to-depth stem): the kw taps of one kernel row are kw CONSECUTIVE pixels of 64/kw channels each,
+  // i.e. one contiguous 128-byte run -- a tensor map whose pixel stride is smaller than its 64-element inner extent
+  // (overlapping rows) turns that run into one K chunk.  Needs the horizontal zero padding materialised in memory
+  // (source rows are W + kw - 1 .. pixels wide, pw == 0) because a window straddles the row edge.
+  const bool window = g.kt == 1 && g.kw > 1 && S.C * g.kw == 64 && S.ld == S.C && S.coff == 0 && g.pw == 0 &&
+                      !g.transposed && g.st == 1 && S.W >= P.Wd + g.kw - 1 && S.H == P.Hd && S.T == P.Td;
+  if (S.C % 8 != 0 || (taps > 1 && S.C % 64 != 0 && !window)) return false;
   if (P.BN % 32 != 0 || P.BN > 256 || P.n_tiles < 1) return false;
   if (P.Kreal != g.kt * g.kh * g.kw * S.C) return false;
   if (g.sh != 1 || g.sw != 1) return false;
@@ -440,9 +471,10 @@ bool conv_tma_plan(const coclr_conv_t& P, TmaPlan& L, MapSpec& A, MapSpec& O) {
   const long ld2 = (long)S.ld * 2;
   L.BN = P.BN;
   L.N = P.N;
+  L.stacked = (P.npass > 1 && P.BN <= 128 && getenv("COCLR_TMA_NOSTACK") == nullptr) ? 1 : 0;
   L.n_tiles_n = P.n_tiles;
-  L.nc = (S.C + 63) / 64;
-  L.nkc = taps * L.nc;
+  L.nc = window ? 1 : (S.C + 63) / 64;
+  L.nkc = window ? g.kh : taps * L.nc;
   L.sel_dim = -1;
   L.a_c0_step = 64;
   A.elem_bytes = 2;
@@ -458,7 +490,7 @@ bool conv_tma_plan(const coclr_conv_t& P, TmaPlan& L, MapSpec& A, MapSpec& O) {
 
   if (g.kt == 1 && g.kh == 1 && g.kw == 1) {
     // ---- 1x1x1: a plain GEMM over the flattened pixels ----
-    if (g.st != 1) return false;
+    if (g.st != 1 || variant > 0) return false;
     if (S.T != P.Td || S.H != P.Hd || S.W != P.Wd) return false;
     const long M = (long)P.B * P.Td * P.Hd * P.Wd;
     if (M >= (1l << 31)) return false;
@@ -475,15 +507,36 @@ bool conv_tma_plan(const coclr_conv_t& P, TmaPlan& L, MapSpec& A, MapSpec& O) {
     L.type[0].tap[0] = 0;
     L.slab_bytes = 128 * 128;
     L.shift_bytes = 0;
+  } else if (window) {
+    // ---- space-to-depth stem: (1, kh, kw) over 64/kw-channel pixels, one slab serves all kh*kw taps ----
+    static const int kNw[2] = {16, 8}, kNh[2] = {8, 16};
+    if (variant > 1 || g.kh > 8) return false;
+    const int nw = kNw[variant], nh = kNh[variant];
+    if (P.Wd % nw != 0 || P.Hd < nh) return false;
+    box[0] = nw; box[1] = nh;
+    L.ntiles[0] = ceil_div(P.Wd, nw); L.ntiles[1] = ceil_div(P.Hd, nh); L.ntiles[2] = S.T; L.ntiles[3] = P.B;
+    A.dims[0] = 64; A.dims[1] = P.Wd; A.dims[2] = S.H; A.dims[3] = S.T; A.dims[4] = P.B;
+    A.strides[0] = ld2; A.strides[1] = ld2 * S.W; A.strides[2] = ld2 * S.W * S.H; A.strides[3] = ld2 * S.W * S.H * S.T;
+    A.box[0] = 64; A.box[1] = nw; A.box[2] = nh + g.kh - 1; A.box[3] = 1; A.box[4] = 1;
+    O.dims[0] = P.N; O.dims[1] = P.Wd; O.dims[2] = P.Hd; O.dims[3] = P.Td; O.dims[4] = P.B;
+    O.strides[0] = old4; O.strides[1] = old4 * P.Wd; O.strides[2] = old4 * P.Wd * P.Hd;
+    O.strides[3] = old4 * P.Wd * P.Hd * P.Td;
+    L.oext[0] = P.Wd; L.oext[1] = P.Hd; L.oext[2] = P.Td; L.oext[3] = P.B;
+    L.n_types = 1;
+    L.a_c0_step = 0;
+    L.type[0].d[1] = -g.ph;
+    L.type[0].nshift = g.kh;
+    for (int j = 0; j < g.kh; ++j) L.type[0].tap[j] = j;     // K chunk ya = the kw taps of kernel row ya
+    L.slab_bytes = nw * (nh + g.kh - 1) * 128;
+    L.shift_bytes = nw * 128;
   } else if (g.kt == 1) {
     // ---- (1, kh, kw), stride 1: dy taps share one slab, one slab type per dx ----
     if (g.st != 1 || g.kw > 4 || g.kh > 8) return false;
     if (S.T != P.Td || S.H != P.Hd || S.W != P.Wd) return false;
-    int nw, nh;
-    if (S.W % 16 == 0) { nw = 16; nh = 8; }
-    else if (S.W % 8 == 0) { nw = 8; nh = 16; }
-    else return false;
-    if (S.H < nh) return false;
+    static const int kNw[3] = {16, 8, 32}, kNh[3] = {8, 16, 4};
+    if (variant > 2) return false;
+    const int nw = kNw[variant], nh = kNh[variant];
+    if (S.W % nw != 0 || S.H < nh) return false;
     box[0] = nw; box[1] = nh;
     L.ntiles[0] = ceil_div(S.W, nw); L.ntiles[1] = ceil_div(S.H, nh); L.ntiles[2] = S.T; L.ntiles[3] = P.B;
     A.dims[0] = S.C; A.dims[1] = S.W; A.dims[2] = S.H; A.dims[3] = S.T; A.dims[4] = P.B;
@@ -511,11 +564,11 @@ bool conv_tma_plan(const coclr_conv_t& P, TmaPlan& L, MapSpec& A, MapSpec& O) {
     if (g.kt > 8) return false;
     if (S.H != P.Hd || S.W != P.Wd) return false;
     const int HW = S.H * S.W;
-    int npx, nt;
+    static const int kNpx[3] = {16, 8, 32}, kNt[3] = {8, 16, 4};
+    if (variant > 2) return false;
+    const int npx = kNpx[variant], nt = kNt[variant];
     const int t_tiles_over = (g.st == 1) ? P.Td : (tr ? P.Td / 2 : P.Td);
-    if (HW % 16 == 0 && t_tiles_over >= 8) { npx = 16; nt = 8; }
-    else if (HW % 32 == 0 && t_tiles_over >= 4) { npx = 32; nt = 4; }
-    else return false;
+    if (HW % npx != 0 || 2 * t_tiles_over < nt + 1) return false;   // at most half a tile of temporal overhang
     box[0] = npx; box[2] = nt;
     const long oHW = (long)P.Hd * P.Wd;
     if (g.st == 1) {
@@ -694,6 +747,26 @@ bool conv_tma_plan(const coclr_conv_t& P, TmaPlan& L, MapSpec& A, MapSpec& O) {
   }
   (void)steps_per_tile;
   return true;
+}
+
+// Tries the tile-shape variants of the launch's kind and keeps the best: double-buffered epilogue staging first, then
+// the deeper A ring, then the smaller slab.
+bool conv_tma_plan(const coclr_conv_t& P, TmaPlan& L, MapSpec& A, MapSpec& O) {
+  bool have = false;
+  long best = -1;
+  for (int v = 0; v < 3; ++v) {
+    TmaPlan l;
+    MapSpec a, o;
+    if (!conv_tma_plan_variant(P, v, l, a, o)) continue;
+    const int slots = l.a_slots < 3 ? l.a_slots : 3;
+    const long score = (long)(l.stage_bufs == 2) * (1l << 40) + (long)slots * (1l << 32) + ((1l << 31) - l.slab_bytes);
+    if (!have || score > best) {
+      have = true;
+      best = score;
+      L = l; A = a; O = o;
+    }
+  }
+  return have;
 }
 
 }  // namespace coclr

@@ -726,7 +726,7 @@ template <int Cin>
 __global__ void __launch_bounds__(256) pack_input_s2d_kernel(const float* x, long batch_stride, long chan_stride,
                                                              uint16_t* out_hi, uint16_t* out_lo,
                                                              uint16_t* out2_hi, uint16_t* out2_lo, int B, int T, int H,
-                                                             int W, const long* __restrict__ batch_index,
+                                                             int W, int pad_x, const long* __restrict__ batch_index,
                                                              const float* const* __restrict__ peer_x, int cpp,
                                                              const float* __restrict__ nmean,
                                                              const float* __restrict__ nstd) {
@@ -772,7 +772,8 @@ __global__ void __launch_bounds__(256) pack_input_s2d_kernel(const float* x, lon
         l2[j] = (uint32_t)b | ((uint32_t)d << 16);
       }
     }
-    const size_t o = (size_t)i * 16;
+    // output rows are W2 + 2*pad_x pixels wide; the pad pixels are never written (the caller zeroes them once)
+    const size_t o = ((size_t)(i / W2) * (size_t)(W2 + 2 * pad_x) + (size_t)(X + pad_x)) * 16;
     auto st32 = [](uint16_t* p, size_t off, const uint32_t* w) {
       uint4* q = reinterpret_cast<uint4*>(p + off);
       q[0] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -1025,10 +1026,10 @@ extern "C" int coclr_pack_input(const float* x, long batch_stride, long chan_str
 }
 
 extern "C" int coclr_pack_input_s2d(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi,
-                                    void* out_lo, void* out2_hi, void* out2_lo, int B, int T, int H, int W,
+                                    void* out_lo, void* out2_hi, void* out2_lo, int B, int T, int H, int W, int pad_x,
                                     const long* batch_index, const void* const* peer_x, int clips_per_peer,
                                     const float* norm_mean, const float* norm_std, coclr_stream_t stream) {
-  if ((!x && !peer_x) || !out_hi || Cin < 1 || Cin > 4 || (H & 1) || (W & 1) || (!norm_mean != !norm_std))
+  if ((!x && !peer_x) || !out_hi || Cin < 1 || Cin > 4 || (H & 1) || (W & 1) || (!norm_mean != !norm_std) || pad_x < 0)
     return COCLR_E_ARG;
   if (peer_x && (!batch_index || clips_per_peer < 1)) return COCLR_E_ARG;
   const long total = (long)B * T * (H / 2) * (W / 2);
@@ -1036,7 +1037,7 @@ extern "C" int coclr_pack_input_s2d(const float* x, long batch_stride, long chan
 #define COCLR_PACK_S2D(CIN)                                                                                         \
   pack_input_s2d_kernel<CIN><<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(                    \
       x, batch_stride, chan_stride, reinterpret_cast<uint16_t*>(out_hi), reinterpret_cast<uint16_t*>(out_lo),       \
-      reinterpret_cast<uint16_t*>(out2_hi), reinterpret_cast<uint16_t*>(out2_lo), B, T, H, W, batch_index,          \
+      reinterpret_cast<uint16_t*>(out2_hi), reinterpret_cast<uint16_t*>(out2_lo), B, T, H, W, pad_x, batch_index,   \
       reinterpret_cast<const float* const*>(peer_x), clips_per_peer, norm_mean, norm_std)
   switch (Cin) {
     case 1: COCLR_PACK_S2D(1); break;

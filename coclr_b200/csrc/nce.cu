@@ -116,3 +116,85 @@ extern "C" int coclr_nce_logits_bwd(const float* dlogits, const float* k, const 
   nce_bwd_kernel<<<B, kNceThreads, smem, (cudaStream_t)stream>>>(dlogits, k, queue, T, D, K, dq);
   return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
 }
+
+// ------------------------------------------------------------------------------------------------
+// CoCLR positive mining (model/pretrain.py:392-413): mask[b, 0] = 1; mask[b, 1+j] = same video source
+// (k_vsource[b] == queue_vname[j]) OR j among the top-k of kf[b] . queue_second[:, j] over the columns that are
+// NOT same-source (the reference writes -inf there before torch.topk).  One CTA per row: similarities into shared
+// memory, then k rounds of a block-wide arg-max (ties: lowest index).  Replaces a cuBLAS GEMM + 5 ATen kernels.
+// ------------------------------------------------------------------------------------------------
+namespace coclr {
+
+__global__ void __launch_bounds__(256) mask_topk_kernel(const float* __restrict__ kf, const float* __restrict__ queue2,
+                                                        const long* __restrict__ vsrc, const long* __restrict__ qvname,
+                                                        int D, int K, int topk, unsigned char* __restrict__ mask) {
+  extern __shared__ float sm[];
+  float* sim = sm;                 // [K]
+  float* sq = sm + K;              // [D]
+  float* redv = sq + D;            // [8]
+  int* redi = reinterpret_cast<int*>(redv + 8);   // [8]
+  const int b = blockIdx.x;
+  unsigned char* mrow = mask + (size_t)b * (size_t)(K + 1);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) sq[c] = kf[(size_t)b * D + c];
+  __syncthreads();
+  const long mine = vsrc[b];
+  if (threadIdx.x == 0) mrow[0] = 1;
+  for (int j = threadIdx.x; j < K; j += blockDim.x) {
+    const bool same = qvname[j] == mine;
+    float a = 0.f;
+    if (topk > 0) {
+#pragma unroll 8
+      for (int c = 0; c < D; ++c) a = fmaf(sq[c], __ldg(queue2 + (size_t)c * K + j), a);
+    }
+    sim[j] = same ? -INFINITY : a;
+    mrow[1 + j] = same ? 1 : 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int r = 0; r < topk; ++r) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+      const float v = sim[j];
+      if (v > bv) { bv = v; bi = j; }        // ascending j per thread: the first maximum wins
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { redv[w] = bv; redi[w] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float v = redv[0];
+      int i = redi[0];
+      for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
+        if (redv[k] > v || (redv[k] == v && redi[k] < i)) { v = redv[k]; i = redi[k]; }
+      redi[0] = (v == -INFINITY) ? -1 : i;    // nothing but masked columns left: those are positives already
+    }
+    __syncthreads();
+    const int sel = redi[0];
+    __syncthreads();
+    if (sel < 0) break;
+    if (threadIdx.x == 0) {
+      mrow[1 + sel] = 1;
+      sim[sel] = -INFINITY;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace coclr
+
+extern "C" int coclr_mask_topk(const float* kf, const float* queue_second, const long* k_vsource, const long* queue_vname,
+                               int B, int D, int K, int topk, unsigned char* mask, coclr_stream_t stream) {
+  if (!k_vsource || !queue_vname || !mask || B <= 0 || K <= 0 || topk < 0) return COCLR_E_ARG;
+  if (topk > 0 && (!kf || !queue_second || D <= 0)) return COCLR_E_ARG;
+  const size_t smem = ((size_t)K + (size_t)D + 16) * sizeof(float);
+  if (smem > 200 * 1024) return COCLR_E_ARG;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(coclr::mask_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return COCLR_E_LAUNCH;
+  coclr::mask_topk_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(kf, queue_second, k_vsource, queue_vname, D, K, topk, mask);
+  return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
+}

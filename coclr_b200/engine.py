@@ -22,6 +22,7 @@ from .s3d_spec import s3d_stages, S3D_FEATURE_SIZE
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+S2D_PAD = 2   # zero pixels kept on either side of every row of the space-to-depth input planes (= the 4x4 stem's padding)
 
 # name -> (fwd_npass, fwd_bf16, bwd_npass): forward planes fp16 (hi/lo) or bf16; gradients are always bf16 planes
 PRECISIONS = {
@@ -147,7 +148,7 @@ class Graph:
                 cv = self._conv(pre + cname, x, y, 0, cin, cout, tuple(k), tuple(s), tuple(p), need_dgrad=not first_conv)
                 if s2d:
                     cv.s2d, cv.cin_eff = True, 4 * cin
-                    cv.k_eff, cv.s_eff, cv.p_eff = (k[0], 4, 4), (s[0], 1, 1), (p[0], 2, 2)
+                    cv.k_eff, cv.s_eff, cv.p_eff = (k[0], 4, 4), (s[0], 1, 1), (p[0], 2, 2 - S2D_PAD)
                 first_conv = False
                 y.bn_members.append((pre + bname, 0, cout))
                 self.items.append(("bn", y))
@@ -192,7 +193,7 @@ class Graph:
         if src_coff or cin != x.C and x is not self.input:
             cv.src_coff, cv.src_C = src_coff, cin
         if s2d:
-            cv.s2d, cv.cin_eff, cv.k_eff, cv.s_eff, cv.p_eff = True, 4 * cin, (1, 4, 4), (1, 1, 1), (0, 2, 2)
+            cv.s2d, cv.cin_eff, cv.k_eff, cv.s_eff, cv.p_eff = True, 4 * cin, (1, 4, 4), (1, 1, 1), (0, 2, 2 - S2D_PAD)
         mid.bn_members.append((name + ".bn1", 0, cout))
         self.items.append(("bn", mid))
         own = dst is None
@@ -428,10 +429,16 @@ class Plan:
             a.spec, a.dims = t, t.dims_fn((T, H, W))
             a.M = B * a.dims[0] * a.dims[1] * a.dims[2]
             shape = (B,) + a.dims + (t.C,)
-            a.pl = ops.Planes(shape, fbf, dev, lo=fnp > 1)          # what every forward consumer reads
+            # the space-to-depth input keeps the stem's horizontal zero padding in memory (rows of W + 2*S2D_PAD pixels,
+            # written once here and never touched by the packing kernel): see coclr_pack_input_s2d
+            padded = g.stem_s2d and t is g.input
+            if padded:
+                shape = (B,) + a.dims[:2] + (a.dims[2] + 2 * S2D_PAD, t.C)
+            a.pl = ops.Planes(shape, fbf, dev, lo=fnp > 1, zero=padded)   # what every forward consumer reads
             # bf16 twin for the weight-gradient GEMM (tcgen05 kind::f16 needs one format for both operands and
             # the output gradients are bf16); not needed when the forward planes already are bf16
-            a.plw = ops.Planes(shape, 1, dev, lo=bnp > 1) if (with_backward and not fbf) else (a.pl if with_backward else None)
+            a.plw = (ops.Planes(shape, 1, dev, lo=bnp > 1, zero=padded) if (with_backward and not fbf)
+                     else (a.pl if with_backward else None))
             a.data = a.grad = a.dy = a.idx = a.bsums = None
             a.grad_written = False
             if t.pending:
@@ -454,9 +461,12 @@ class Plan:
         self.input = acts[g.input.index]
         st = eng.store
 
+        def src_w(a):
+            return a.dims[2] + (2 * S2D_PAD if (g.stem_s2d and a.spec is g.input) else 0)
+
         def src_of(a, it=None):
             coff, cc = (it.src_coff, it.src_C) if it is not None else (0, a.spec.C)
-            return a.pl.src(coff, cc, a.dims[0], a.dims[1], a.dims[2])
+            return a.pl.src(coff, cc, a.dims[0], a.dims[1], src_w(a))
 
         # which channel ranges of a tensor's gradient buffer already hold a value (first writer stores, later ones add)
         grad_ranges = {}
@@ -630,7 +640,7 @@ class Plan:
                     # ... and every split should own >= 16 pixel chunks: each split ends with Cout x K fp32 atomics,
                     # which dominate when the pixel range per CTA is short
                     splits = max(1, min(chunks // 16 if chunks >= 16 else 1, (2 * nsm) // tiles))
-                    wsrc = sa.plw.src(it.src_coff, it.src_C, sa.dims[0], sa.dims[1], sa.dims[2])
+                    wsrc = sa.plw.src(it.src_coff, it.src_C, sa.dims[0], sa.dims[1], src_w(sa))
                     if it.s2d:
                         # the weight gradient is produced in the space-to-depth layout, then scattered back
                         dw_eff = eng.s2d[it.name]["dw_eff"]
@@ -852,7 +862,7 @@ class EncoderEngine:
             assert H % 2 == 0 and W % 2 == 0, "the space-to-depth stem needs even H, W"
             L.check(lib.coclr_pack_input_s2d(L.dptr(x), x.stride(0), x.stride(1), Cin, L.dptr(p.input.pl.hi),
                                              L.dptr(p.input.pl.lo), L.dptr(tw.hi) if tw else None,
-                                             L.dptr(tw.lo) if tw else None, B, T, H, W, L.dptr(batch_index),
+                                             L.dptr(tw.lo) if tw else None, B, T, H, W, S2D_PAD, L.dptr(batch_index),
                                              peer_ptr, cpp, nm, ns, L.stream_ptr()), "coclr_pack_input_s2d")
         else:
             L.check(lib.coclr_pack_input(L.dptr(x), x.stride(0), x.stride(1), Cin, L.dptr(p.input.pl.hi),

@@ -169,6 +169,21 @@ def enqueue(queue, keys, ptr):
             "coclr_queue_enqueue")
 
 
+@torch.no_grad()
+def mask_topk(kf, queue_second, k_vsource, queue_vname, topk):
+    """CoCLR's positive mask [B, 1+K] bool (model/pretrain.py:392-413): column 0 and the same-source columns, plus --
+    when topk > 0 -- the top-k columns of kf @ queue_second among the others."""
+    B, K = k_vsource.shape[0], queue_vname.shape[0]
+    assert k_vsource.dtype == torch.long and queue_vname.dtype == torch.long
+    mask = torch.empty(B, K + 1, dtype=torch.bool, device=k_vsource.device)
+    kf = kf.contiguous()
+    assert queue_second.is_contiguous() and kf.shape[1] == queue_second.shape[0]
+    L.check(L.load().coclr_mask_topk(L.dptr(kf), L.dptr(queue_second), L.dptr(k_vsource.contiguous()),
+                                     L.dptr(queue_vname), B, kf.shape[1], K, int(topk), L.dptr(mask), L.stream_ptr()),
+            "coclr_mask_topk")
+    return mask
+
+
 class _NCELogitsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, queue, T):

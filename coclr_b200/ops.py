@@ -28,11 +28,12 @@ class Geometry:
 class Planes:
     """A split-precision channels-last activation: two 16-bit planes [B,T,H,W,C] with hi + lo ~= value."""
 
-    def __init__(self, shape, bf16, device, lo=True):
+    def __init__(self, shape, bf16, device, lo=True, zero=False):
         dt = torch.bfloat16 if bf16 else torch.float16
         self.bf16 = int(bool(bf16))
-        self.hi = torch.empty(shape, dtype=dt, device=device)
-        self.lo = torch.empty(shape, dtype=dt, device=device) if lo else None
+        mk = torch.zeros if zero else torch.empty
+        self.hi = mk(shape, dtype=dt, device=device)
+        self.lo = mk(shape, dtype=dt, device=device) if lo else None
 
     @property
     def ld(self):

@@ -241,10 +241,13 @@ int coclr_pack_input(const float* x, long batch_stride, long chan_stride, int Ci
                      const float* norm_mean, const float* norm_std /* device [Cin] or both NULL */,
                      coclr_stream_t stream);
 
-/* space-to-depth variant for the stride-2 7x7 RGB stem (backbone/s3dg.py:145): planes [B, T, H/2, W/2, 16] with
- * channel (dy*2+dx)*Cin + c = x[b, c, t, 2Y+dy, 2X+dx] (4*Cin real channels, rest zero); H, W even */
+/* space-to-depth variant for the stride-2 7x7 RGB stem (backbone/s3dg.py:145): planes [B, T, H/2, W/2 + 2*pad_x, 16]
+ * with channel (dy*2+dx)*Cin + c = x[b, c, t, 2Y+dy, 2X+dx] (4*Cin real channels, rest zero) at pixel X + pad_x of a
+ * row; H, W even.  The pad_x pixels on either side of a row are NOT written: the caller zeroes the planes once, which
+ * materialises the conv's horizontal zero padding (pad_x = 2 for the 4x4 stem) so that the four taps of a kernel row
+ * are one contiguous 128-byte run for every output pixel (the TMA window operand of csrc/conv_tma.cu). */
 int coclr_pack_input_s2d(const float* x, long batch_stride, long chan_stride, int Cin, void* out_hi, void* out_lo,
-                         void* out2_hi, void* out2_lo, int B, int T, int H, int W, const long* batch_index,
+                         void* out2_hi, void* out2_lo, int B, int T, int H, int W, int pad_x, const long* batch_index,
                          const void* const* peer_x, int clips_per_peer, const float* norm_mean, const float* norm_std,
                          coclr_stream_t stream);
 
@@ -281,6 +284,14 @@ int coclr_nce_logits_ce(const float* q, const float* k, const float* queue, floa
 /* dq = d(logits)^T contraction with [k | queue] / T (no gradient to k or the queue, pretrain.py:160,176) */
 int coclr_nce_logits_bwd(const float* dlogits, const float* k, const float* queue, float T, int B, int D, int K,
                          float* dq, coclr_stream_t stream);
+
+/* ---- CoCLR positive mining (model/pretrain.py:392-413): same-source mask OR top-k of the second view's similarity ----
+ * mask[b, 0] = 1; mask[b, 1+j] = (k_vsource[b] == queue_vname[j]) OR j in top-`topk` of kf[b] . queue_second[:, j] taken
+ * over the columns that are not same-source (the reference fills those with -inf before torch.topk, :406-407).
+ * topk == 0 (or a queue that is not full yet, :404): same-source mask only; kf / queue_second may then be NULL.
+ * mask: [B, 1+K] bytes (torch.bool storage). */
+int coclr_mask_topk(const float* kf, const float* queue_second, const long* k_vsource, const long* queue_vname, int B, int D,
+                    int K, int topk, unsigned char* mask, coclr_stream_t stream);
 
 #ifdef __cplusplus
 }

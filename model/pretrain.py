@@ -238,34 +238,45 @@ class CoCLR(InfoNCE):
         self.queue_is_full = False
         self.reverse = reverse
 
+    overlap_branches = True   # query, key and sampler encoders on three streams (they only share read-only inputs)
+
     def forward(self, block1, block2, k_vsource):
         x1, f1 = self._views(block1)
         x2, f2 = self._views(block2)
         if self.reverse:                                                              # :353-355
             x1, f1 = f1, x1
             x2, f2 = f2, x2
-        q = self.encoder_q.encode(x1)
-        in_train_mode = q.requires_grad
-        with torch.no_grad():
+        if not x1.is_cuda:
+            raise moco.L.CoclrError("coclr_b200 modules run on CUDA (sm_100a) only; there is no CPU path")
+        in_train_mode = torch.is_grad_enabled() and any(p.requires_grad for p in self.encoder_q.parameters())
+        main = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream()
+        if getattr(self, "_side_stream2", None) is None:
+            self._side_stream2 = torch.cuda.Stream()
+        side = self._side_stream if CoCLR.overlap_branches else main
+        side2 = self._side_stream2 if CoCLR.overlap_branches else main
+        side.wait_stream(main)
+        side2.wait_stream(main)
+        with torch.cuda.stream(side), torch.no_grad():
             if in_train_mode:
                 self._momentum_update_key_encoder()
             k, k_global = self._shuffled_keys(x2)
+        with torch.cuda.stream(side2), torch.no_grad():
             kf = self.sampler.encode(f2)                                              # :372-374 (no shuffle)
+        q = self.encoder_q.encode(x1)
+        main.wait_stream(side)
+        main.wait_stream(side2)
+        for t in (k, k_global, kf):
+            t.record_stream(main)
         logits = moco.nce_logits(q, k, self.queue, self.T)
-        mask_source = k_vsource.unsqueeze(1) == self.queue_vname.unsqueeze(0)         # :392
-        mask = mask_source.clone()
         if not self.queue_is_full:
             self.queue_is_full = bool(torch.all(self.queue_label != -1))              # :400-402
             if self.queue_is_full:
                 print('\n===== queue is full now =====')
-        if self.queue_is_full and (self.topk != 0):                                   # :404-410
-            mask_sim = kf.matmul(self.queue_second.clone().detach())
-            mask_sim[mask_source] = - np.inf
-            _, topkidx = torch.topk(mask_sim, self.topk, dim=1)
-            topk_onehot = torch.zeros_like(mask_sim)
-            topk_onehot.scatter_(1, topkidx, 1)
-            mask[topk_onehot.bool()] = True
-        mask = torch.cat([torch.ones((mask.shape[0], 1), dtype=torch.bool, device=mask.device), mask], dim=1)
+        # same-source positives OR the top-k of the second view's similarity (:392-413), one fused kernel
+        mask = moco.mask_topk(kf, self.queue_second, k_vsource, self.queue_vname,
+                              self.topk if self.queue_is_full else 0)
         if in_train_mode:
             with torch.no_grad():
                 kf_global = concat_all_gather(kf)
@@ -275,4 +286,4 @@ class CoCLR(InfoNCE):
                 moco.enqueue(self.queue_second, kf_global.contiguous(), ptr)          # :334
                 self.queue_vname[ptr:ptr + n] = vn_global                             # :335
                 self.queue_label[ptr:ptr + n] = torch.ones_like(vn_global)            # :336
-        return logits, mask.detach()
+        return logits, mask

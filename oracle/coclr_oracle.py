@@ -188,13 +188,16 @@ def momentum_update(sd, m):
         sd[kk] = sd[kk] * m + sd[kq].detach() * (1. - m)
 
 
-def infonce_forward(sd, blocks, idx_shuffle, m=0.999, T=0.07, training=True):
+def infonce_forward(sd, blocks, idx_shuffle, m=0.999, T=0.07, training=True, keep_graph=True):
     """InfoNCE.forward for a simulated world of len(blocks) ranks sharing `sd`; model/pretrain.py:145-190.
 
     blocks: list (one per rank) of [B,2,C,T,H,W]; idx_shuffle: the permutation rank 0 would broadcast
     (pretrain.py:112-115).  Returns (list of logits per rank, labels).  Side effects on sd as in the
     reference: EMA of encoder_k (:161), BN running statistics, queue / queue_ptr (:82-96).
     BN buffers tracked are rank 0's (DDP re-broadcasts rank 0's buffers before every forward).
+    keep_graph=False (checker use only, e.g. bench.py's parity block over 8 simulated ranks): the query features are
+    detached as soon as they are computed, so that only one encoder pass of activations is alive at a time; every
+    value and side effect is the same, only backward through the returned logits is unavailable.
     """
     W = len(blocks)
     B = blocks[0].shape[0]
@@ -203,11 +206,14 @@ def infonce_forward(sd, blocks, idx_shuffle, m=0.999, T=0.07, training=True):
         assert blk.shape[1] == 2                                                    # :148
     # queries (:153-155); BN buffer side effects kept for rank 0 only
     qs = []
+    in_train_mode = None
     for r, blk in enumerate(blocks):
         sdr = sd if r == 0 else _bn_scratch(sd, "encoder_q.")
         q = encoder(sdr, "encoder_q.", blk[:, 0].contiguous(), training)
-        qs.append(F.normalize(q, dim=1).view(B, dim))
-    in_train_mode = qs[0].requires_grad                                             # :157
+        q = F.normalize(q, dim=1).view(B, dim)
+        if in_train_mode is None:
+            in_train_mode = q.requires_grad                                         # :157
+        qs.append(q if keep_graph else q.detach())
     with torch.no_grad():
         if in_train_mode:
             momentum_update(sd, m)                                                  # :161

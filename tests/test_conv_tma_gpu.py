@@ -148,3 +148,42 @@ def test_tma_matches_gather_bitwise_statistics_order_free(diag):
         _run(ops, cv, 1)
         outs.append(dst)
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("npass,bf16", [(3, 0), (1, 1)])
+def test_tma_window_stem(npass, bf16, diag):
+    """The space-to-depth stem (backbone/s3dg.py:145 Conv_1a.conv1 as a stride-1 (1,4,4) conv over 16-channel pixels,
+    engine.py Graph.stem_s2d): the four taps of a kernel row are ONE 128-byte run of the zero-padded input rows, read
+    through a tensor map with overlapping rows; all 16 taps are served by one slab per tile and the weights stay
+    resident.  Same conv on the gather kernel (padded source, pw = 0) as a second opinion."""
+    from coclr_b200 import ops
+    B, T, H2, W2, Cout = 4, 6, 32, 32, 64        # 192 tiles: more than one per SM, so the weights stay resident
+    g = torch.Generator(device="cuda").manual_seed(43)
+    x = torch.randn(B, 16, T, H2, W2, device="cuda", generator=g)
+    x[:, 12:] = 0.0                                           # 4*Cin = 12 real channels
+    w = torch.randn(Cout, 16, 1, 4, 4, device="cuda", generator=g) * 0.05
+    ref = F.conv3d(x.double(), w.double(), padding=(0, 2, 2))[..., :H2, :W2]
+    xpad = F.pad(x, (2, 2))                                   # the layout coclr_pack_input_s2d(pad_x=2) writes
+    pl, Cp, coff = _planes_of(ops, xpad, bf16, ld_extra=0, coff=0, lo=(npass > 1))
+    geom = ops.Geometry((1, 4, 4), (1, 1, 1), (0, 2, 0))
+    pw = ops.PackedWeights(Cout, 16, 16, 16, 0, bf16, "cuda").pack(w.contiguous())
+    errs = {}
+    for tma in (1, 0):
+        dst = torch.full((B, T, H2, W2, Cout), -3.0, device="cuda")
+        stats = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+        cv = ops.make_conv(pl.src(0, 16, T, H2, W2 + 4), bf16, geom.c(0), B, (T, H2, W2), pw, dst, 0,
+                           stats_sum=stats[:Cout], stats_sq=stats[Cout:], npass=npass)
+        if tma:
+            ok, info = _takes_tma(cv)
+            diag["tma_plan/window_stem/p%d" % npass] = info
+            assert ok and info[2] == 1, "window stem: planner %s" % info      # TMA kernel, resident weights
+        _run(ops, cv, tma)
+        got = dst.permute(0, 4, 1, 2, 3)
+        errs[tma] = _rel(got, ref)
+        if tma:
+            s1 = got.double().sum(dim=(0, 2, 3, 4))
+            assert float((stats[:Cout] - s1).abs().max() / s1.abs().max()) < 1e-5
+    diag["tma_fwd/window_stem/p%d" % npass] = [errs[1], errs[0]]
+    tol = 2e-5 if npass == 3 and not bf16 else 3e-2
+    assert errs[0] < tol, "gather kernel on the padded stem input: %.3e" % errs[0]
+    assert errs[1] < tol, "TMA window stem: %.3e (gather: %.3e)" % (errs[1], errs[0])

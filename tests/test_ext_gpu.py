@@ -123,3 +123,48 @@ def test_graph_replay_matches_eager(diag):
     assert errs[0] < 1e-5
     for e, b in zip(errs, base):
         assert e < 10 * b + 2e-3, (errs, base)
+
+
+@pytest.mark.parametrize("K,B,topk", [(2048, 32, 5), (16384, 32, 5), (128, 4, 5), (2048, 8, 0), (64, 3, 7)])
+def test_mask_topk_kernel_matches_reference_statements(K, B, topk, diag):
+    """coclr_mask_topk against the reference's mining code restated line by line (model/pretrain.py:392-413) on the
+    same device in float64 similarities: same-source mask, -inf fill, torch.topk, one-hot scatter, OR, leading ones
+    column.  Includes a row whose queue entries are ALL same-source (top-k then only re-selects positives) and rows
+    with fewer than k other-source columns."""
+    from coclr_b200 import moco
+    g = torch.Generator(device="cuda").manual_seed(K + B)
+    D = 128
+    kf = torch.nn.functional.normalize(torch.randn(B, D, device="cuda", generator=g), dim=1)
+    q2 = torch.nn.functional.normalize(torch.randn(D, K, device="cuda", generator=g), dim=0)
+    vsrc = torch.randint(0, 40, (B,), device="cuda", generator=g)
+    qv = torch.randint(0, 40, (K,), device="cuda", generator=g)
+    vsrc[0] = 1000                                    # row 0: no same-source column at all
+    if B > 1:
+        vsrc[1] = 7
+        qv2 = qv.clone()
+        qv2[3:] = 7                                   # row 1: all but three columns are same-source (< k candidates)
+    else:
+        qv2 = qv
+    for qvn in (qv, qv2):
+        got = moco.mask_topk(kf, q2, vsrc, qvn, topk)
+        torch.cuda.synchronize()
+        mask_source = vsrc.unsqueeze(1) == qvn.unsqueeze(0)                           # :392
+        mask = mask_source.clone()
+        if topk != 0:                                                                # :404-410
+            mask_sim = kf.double().matmul(q2.double())
+            mask_sim[mask_source] = -np.inf
+            _, topkidx = torch.topk(mask_sim, min(topk, K), dim=1)
+            topk_onehot = torch.zeros_like(mask_sim)
+            topk_onehot.scatter_(1, topkidx, 1)
+            # torch.topk returns masked (-inf) columns when fewer than k candidates remain; those are positives already
+            mask[topk_onehot.bool()] = True
+        want = torch.cat([torch.ones((B, 1), dtype=torch.bool, device="cuda"), mask], dim=1)   # :412
+        assert got.dtype == torch.bool and got.shape == (B, 1 + K)
+        if topk != 0:   # -inf picks of torch.topk are arbitrary masked columns: compare on what is defined
+            finite_ok = torch.equal(got[:, 1:] & ~mask_source, want[:, 1:] & ~mask_source)
+            assert finite_ok
+            assert torch.equal(got[:, 1:] & mask_source, mask_source)
+            assert bool(got[:, 0].all())
+        else:
+            assert torch.equal(got, want)
+    diag["mask_topk/K%d_B%d_k%d" % (K, B, topk)] = "bit-exact"

@@ -18,7 +18,18 @@ To, Ho, Wo = geom.out_dims(T, H, W)
 dev = "cuda"
 r8 = lambda c: (c + 7) // 8 * 8
 w = torch.randn(Cout, Cin, kt, kh, kw, device=dev) * 0.05
-if mode == "fwd":
+if mode == "s2d":
+    # the space-to-depth stem as the engine launches it: (1,4,4) over 16-channel pixels, zero-padded rows (W + 4), pw = 0
+    geom = ops.Geometry((1, 4, 4), (1, 1, 1), (0, 2, 0))
+    To, Ho, Wo = T, H, W
+    x = ops.Planes((B, T, H, W + 4, 16), 0, dev, zero=True)
+    x.hi[..., 2:-2, :12].normal_(); x.lo[..., 2:-2, :12].normal_(0, 1e-3)
+    w = torch.randn(Cout, 16, 1, 4, 4, device=dev) * 0.05
+    pw = ops.PackedWeights(Cout, 16, 16, 16, 0, 0, dev).pack(w)
+    dst = torch.empty(B, To, Ho, Wo, Cout, device=dev)
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
+    run = lambda: ops.conv_igemm(x.src(0, 16, T, H, W + 4), 0, geom.c(0), B, (To, Ho, Wo), pw, dst, stats=stats, npass=npass)
+elif mode == "fwd":
     x = ops.Planes((B, T, H, W, r8(Cin)), 0, dev)
     x.hi.normal_(); x.lo.normal_(0, 1e-3)
     pw = ops.PackedWeights(Cout, Cin, geom.taps, r8(Cin), 0, 0, dev).pack(w)
