@@ -15,6 +15,7 @@ EXPORTS = {
     "coclr_set_conv_tma": (None, [I]),
     "coclr_conv_wgrad": (I, [P, P]),
     "coclr_pack_weights": (I, [P, P]),
+    "coclr_pack_weights_batch": (I, [P, P, I, I, P]),
     "coclr_affine_split": (I, [P, I, P]),
     "coclr_bn_finalize": (I, [P, P]),
     "coclr_bn_bwd": (I, [P, I, P]),

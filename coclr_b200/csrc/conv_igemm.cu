@@ -371,6 +371,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const coclr_con
           const float4 u4 = __ldg(reinterpret_cast<const float4*>(P.wunscale + n_tile * P.BN + c0 + cq * 4));
           us[0] = u4.x; us[1] = u4.y; us[2] = u4.z; us[3] = u4.w;
         }
+        if (P.out_scale != nullptr) {
+          const float os = __ldg(P.out_scale);
+          us[0] *= os; us[1] *= os; us[2] *= os; us[3] *= os;
+        }
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
         const bool full_quad = colq + 3 < P.N;
         if (colq < P.N) {
@@ -644,6 +648,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
       mbar_wait(&tfull_bar[0], 0);
       tc_fence_after();
       const int n = c_tile * 128 + warp * 32 + lane;  // output channel of this thread
+      const float os = P.out_scale != nullptr ? __ldg(P.out_scale) : 1.f;
       for (int c0 = 0; c0 < BNk; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
@@ -656,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
               const int tap = k / P.src.C;
               const int ci = k - tap * P.src.C;
               if (ci < P.Cin_real)
-                atomicAdd(P.dw + ((size_t)n * P.Cin_real + ci) * taps + tap, __uint_as_float(v[j]));
+                atomicAdd(P.dw + ((size_t)n * P.Cin_real + ci) * taps + tap, __uint_as_float(v[j]) * os);
             }
           }
         }
@@ -676,12 +681,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
 // weight packer: one CTA per packed row
 // ------------------------------------------------------------------------------------------------
 template <bool kBf16>
-__global__ void pack_weights_kernel(const coclr_pack_t P, int N, int BN, int n_tiles, int Kreal, int nkc) {
-  const int row = blockIdx.x;  // 0 .. n_tiles*BN
+COCLR_DEVINL void pack_row(const coclr_pack_t& P, int N, int BN, int Kreal, int nkc, int row, float* red) {
   const int n_tile = row / BN;
   const int rin = row - n_tile * BN;
   const int n = n_tile * BN + rin;  // tiles are contiguous in n
-  __shared__ float red[32];
   const int Kpad = nkc * kChunkK;
   auto wval = [&](int k) -> float {
     if (n >= N || k >= Kreal) return 0.f;
@@ -730,12 +733,48 @@ __global__ void pack_weights_kernel(const coclr_pack_t P, int N, int BN, int n_t
   }
 }
 
-static inline void tile_plan(int N, int* BN, int* n_tiles) {
+template <bool kBf16>
+__global__ void pack_weights_kernel(const coclr_pack_t P, int N, int BN, int n_tiles, int Kreal, int nkc) {
+  __shared__ float red[32];
+  pack_row<kBf16>(P, N, BN, Kreal, nkc, blockIdx.x, red);
+}
+
+__host__ __device__ inline void tile_plan_hd(int N, int* BN, int* n_tiles) {
   int nt = (N + 255) / 256;
   int w = (N + nt - 1) / nt;
   *BN = ((w + 31) / 32) * 32;
   *n_tiles = nt;
 }
+
+// All weights of an encoder in ONE launch: CTA r packs global row r; row_start[i] = first row of table entry i
+// (ascending, row_start[n] = total rows).  Replaces ~100 launches per encoder pass.
+__global__ void pack_weights_batch_kernel(const coclr_pack_t* __restrict__ table, const int* __restrict__ row_start,
+                                          int n) {
+  __shared__ float red[32];
+  __shared__ coclr_pack_t P;
+  __shared__ int s_first;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n - 1;              // last entry whose first row is <= blockIdx.x
+    const int r = (int)blockIdx.x;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (row_start[mid] <= r) lo = mid; else hi = mid - 1;
+    }
+    P = table[lo];
+    s_first = row_start[lo];
+  }
+  __syncthreads();
+  const int N = P.mode == 0 ? P.Cout : P.Cin;
+  const int Kreal = P.taps * P.Cpad;
+  int BN, nt;
+  tile_plan_hd(N, &BN, &nt);
+  const int nkc = (Kreal + kChunkK - 1) / kChunkK;
+  const int row = (int)blockIdx.x - s_first;
+  if (P.bf16) pack_row<true>(P, N, BN, Kreal, nkc, row, red);
+  else pack_row<false>(P, N, BN, Kreal, nkc, row, red);
+}
+
+static inline void tile_plan(int N, int* BN, int* n_tiles) { tile_plan_hd(N, BN, n_tiles); }
 
 }  // namespace coclr
 
@@ -762,6 +801,13 @@ extern "C" int coclr_pack_weights(const coclr_pack_t* p, coclr_stream_t stream) 
     pack_weights_kernel<true><<<nt * BN, 128, 0, s>>>(*p, N, BN, nt, Kreal, nkc);
   else
     pack_weights_kernel<false><<<nt * BN, 128, 0, s>>>(*p, N, BN, nt, Kreal, nkc);
+  return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
+}
+
+extern "C" int coclr_pack_weights_batch(const coclr_pack_t* table_dev, const int* row_start_dev, int n, int total_rows,
+                                        coclr_stream_t stream) {
+  if (!table_dev || !row_start_dev || n < 1 || total_rows < 1) return COCLR_E_ARG;
+  pack_weights_batch_kernel<<<total_rows, 128, 0, (cudaStream_t)stream>>>(table_dev, row_start_dev, n);
   return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
 }
 

@@ -250,8 +250,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     // the bulk-tensor stores of a warp are issued, committed and waited for by ONE thread (bulk async-groups are
     // per-thread state): elected once (elect.sync is deterministic for a given member mask)
     const bool leader = elect_one();
-    if (P.wunscale != nullptr && L.n_tiles_n == 1) {
-      for (int i = threadIdx.x; i < L.BN; i += 128) unscale_tab[i] = __ldg(P.wunscale + i);
+    const float oscale = P.out_scale != nullptr ? __ldg(P.out_scale) : 1.f;
+    if ((P.wunscale != nullptr || P.out_scale != nullptr) && L.n_tiles_n == 1) {
+      for (int i = threadIdx.x; i < L.BN; i += 128)
+        unscale_tab[i] = (P.wunscale != nullptr ? __ldg(P.wunscale + i) : 1.f) * oscale;
     }
     named_bar_sync(1, 128);
     const uint32_t my_stage = stage_base + (uint32_t)warp * (uint32_t)L.stage_bufs * kStageBytes;
@@ -282,9 +284,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         oc[d] = o + L.sub[warp][d];
       }
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-      if (P.wunscale != nullptr && L.n_tiles_n > 1) {
+      if ((P.wunscale != nullptr || P.out_scale != nullptr) && L.n_tiles_n > 1) {
         named_bar_sync(1, 128);   // previous tile's readers are done with the table
-        for (int i = threadIdx.x; i < L.BN; i += 128) unscale_tab[i] = __ldg(P.wunscale + t.n_tile * L.BN + i);
+        for (int i = threadIdx.x; i < L.BN; i += 128)
+          unscale_tab[i] = (P.wunscale != nullptr ? __ldg(P.wunscale + t.n_tile * L.BN + i) : 1.f) * oscale;
         named_bar_sync(1, 128);
       }
       mbar_wait(&t_full[acc], (it >> 1) & 1u);
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       for (int kq = 0; kq < 8; ++kq) {
         const int c0 = kq * 32;
         const int col0 = t.n_tile * L.BN + c0;
-        if (c0 < L.BN && col0 < L.N) {
+        if (c0 < L.BN && col0 < L.N && !(L.dbg & 4)) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 256u + (uint32_t)c0, v);
           if (kLo && L.stacked) {
@@ -321,13 +324,13 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (leader) {
+          if (leader && !(L.dbg & 1)) {
             if (P.accumulate) tma_reduce_add_5d(&map_out, buf, col0, oc[0], oc[1], oc[2], oc[3]);
             else tma_store_5d(&map_out, buf, col0, oc[0], oc[1], oc[2], oc[3]);
             bulk_commit_group();
           }
           ++nstore;
-          if (want_stats) {
+          if (want_stats && !(L.dbg & 2)) {
             // lane c sums column c over the warp's valid rows, reading the swizzled block back (conflict-free)
             float a = 0.f, b = 0.f;
             const uint32_t cchunk = (uint32_t)lane >> 2, cword = ((uint32_t)lane & 3u) << 2;
@@ -471,6 +474,7 @@ static bool conv_tma_plan_variant(const coclr_conv_t& P, int variant, TmaPlan& L
   const long ld2 = (long)S.ld * 2;
   L.BN = P.BN;
   L.N = P.N;
+  { const char* e = getenv("COCLR_TMA_DBG"); L.dbg = e ? atoi(e) : 0; }
   L.stacked = (P.npass > 1 && P.BN <= 128 && getenv("COCLR_TMA_NOSTACK") == nullptr) ? 1 : 0;
   L.n_tiles_n = P.n_tiles;
   L.nc = window ? 1 : (S.C + 63) / 64;
@@ -816,6 +820,7 @@ int coclr::conv_tma_try(const coclr_conv_t& P, int num_sms, cudaStream_t stream)
   if (!encode_map(&m_out, O, 0)) return 1;
   args.wpk = P.wpk;
   args.wunscale = P.wunscale;
+  args.out_scale = P.out_scale;
   args.stats_sum = P.stats_sum;
   args.stats_sq = P.stats_sq;
   args.accumulate = P.accumulate;

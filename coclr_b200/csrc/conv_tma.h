@@ -35,6 +35,7 @@ struct TmaPlan {
   int a_slots, a_slot_bytes;
   int b_slots, b_tile_bytes, b_resident;
   int stage_bufs;
+  int dbg;             // tuning experiments only (COCLR_TMA_DBG bit mask; 0 in production)
   int stacked;         // 3-pass mode, BN <= 128: hi and lo weight rows form ONE N = 2*BN operand (see the MMA issuer)
   int sub[4][4];       // output coordinate offsets of each epilogue warp's 32-row sub-box
   int BN, N;
@@ -45,6 +46,7 @@ struct TmaArgs {
   TmaPlan plan;
   const void* wpk;
   const float* wunscale;
+  const float* out_scale;
   double* stats_sum;
   double* stats_sq;
   int accumulate;

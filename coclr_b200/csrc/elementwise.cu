@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_reduce_kernel(const coclr_
   __shared__ float red[8][kColThreads];
   const int t = threadIdx.x;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float mx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // max |dz| and max |xhat| per channel (range of dY, see apply)
   if (t < A) {
     const int cg = t % C4, rs = t / C4;
     const int c = K.cb + cg * 4;
@@ -264,11 +265,16 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_reduce_kernel(const coclr_
     const long r_end = min((long)P.M, r_begin + rows_per);
     auto body = [&](long row, const float4& y, const float4& da) {
       const float4 dz = bwd_dz(P, (size_t)row, c, y, da, sc, sh);
+      const float x0 = (y.x - mu.x) * rs4.x, x1 = (y.y - mu.y) * rs4.y, x2 = (y.z - mu.z) * rs4.z, x3 = (y.w - mu.w) * rs4.w;
       acc[0] += dz.x; acc[1] += dz.y; acc[2] += dz.z; acc[3] += dz.w;
-      acc[4] += dz.x * ((y.x - mu.x) * rs4.x);
-      acc[5] += dz.y * ((y.y - mu.y) * rs4.y);
-      acc[6] += dz.z * ((y.z - mu.z) * rs4.z);
-      acc[7] += dz.w * ((y.w - mu.w) * rs4.w);
+      acc[4] += dz.x * x0;
+      acc[5] += dz.y * x1;
+      acc[6] += dz.z * x2;
+      acc[7] += dz.w * x3;
+      mx[0] = fmaxf(mx[0], fabsf(dz.x)); mx[1] = fmaxf(mx[1], fabsf(dz.y));
+      mx[2] = fmaxf(mx[2], fabsf(dz.z)); mx[3] = fmaxf(mx[3], fabsf(dz.w));
+      mx[4] = fmaxf(mx[4], fabsf(x0)); mx[5] = fmaxf(mx[5], fabsf(x1));
+      mx[6] = fmaxf(mx[6], fabsf(x2)); mx[7] = fmaxf(mx[7], fabsf(x3));
     };
     long r = r_begin + rs;
     for (; r + 3 * R < r_end; r += 4 * R) {   // 8 independent 16-byte loads in flight per thread
@@ -297,6 +303,23 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_reduce_kernel(const coclr_
       atomicAdd(P.sums + P.C + K.cb + t * 4 + j, s[4 + j]);
     }
   }
+  if (P.amax != nullptr) {   // block-wide maxima of the two range inputs (non-negative floats order like their bit patterns)
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[j][t] = mx[j];
+    __syncthreads();
+    if (t < C4) {
+      float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < R; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], red[j][t + k * C4]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicMax(reinterpret_cast<int*>(P.amax) + K.cb + t * 4 + j, __float_as_int(m[j]));
+        atomicMax(reinterpret_cast<int*>(P.amax) + P.C + K.cb + t * 4 + j, __float_as_int(m[4 + j]));
+      }
+    }
+  }
 }
 
 // phase 2: dY = scale * (dz - s1/n - xhat * s2/n) -> bf16 hi/lo planes; dres (+)= dz; the first row slab also
@@ -305,11 +328,37 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(const coclr_b
   const BwdCols K = bwd_cols(P);
   const int C4 = K.C4, A = K.A, R = K.R;
   const int t = threadIdx.x;
+  const double inv_n = 1.0 / (double)P.M;
+  // fp16 planes: one power-of-two scale for the whole tensor from |dY_c| <= |scale_c| (max|dz_c| + |m1_c| + max|xhat_c| |m2_c|);
+  // every block derives the same value (the inputs are final after the reduce kernel)
+  float dscale = 1.f;
+  if (P.dy_fp16) {
+    __shared__ float smax[kColThreads / 32];
+    float bound = 0.f;
+    for (int ch = t; ch < P.C; ch += kColThreads) {
+      const float b = fabsf(P.scale[ch]) * (P.amax[ch] + fabsf((float)(P.sums[ch] * inv_n)) +
+                                           P.amax[P.C + ch] * fabsf((float)(P.sums[P.C + ch] * inv_n)));
+      bound = fmaxf(bound, b);
+    }
+    for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+    if ((t & 31) == 0) smax[t >> 5] = bound;
+    __syncthreads();
+    bound = 0.f;
+    for (int k = 0; k < kColThreads / 32; ++k) bound = fmaxf(bound, smax[k]);
+    if (bound > 0.f && isfinite(bound)) {
+      int e;
+      frexpf(bound, &e);                       // bound = f * 2^e, f in [0.5, 1)  ->  bound * 2^(14 - e) < 2^14
+      dscale = ldexpf(1.f, max(-100, min(100, 14 - e)));
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && t == 0 && P.dy_scale != nullptr) {
+      P.dy_scale[0] = dscale;
+      P.dy_scale[1] = 1.f / dscale;
+    }
+  }
   if (t >= A) return;
   const int cg = t % C4, rs = t / C4;
   const int c = K.cb + cg * 4;
   const float4 sc = ld4(P.scale + c), sh = ld4(P.shift + c), mu = ld4(P.mean + c), rs4 = ld4(P.rstd + c);
-  const double inv_n = 1.0 / (double)P.M;
   float m1[4], m2[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -333,7 +382,12 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(const coclr_b
     o.y = sc.y * (dz.y - m1[1] - ((y.y - mu.y) * rs4.y) * m2[1]);
     o.z = sc.z * (dz.z - m1[2] - ((y.z - mu.z) * rs4.z) * m2[2]);
     o.w = sc.w * (dz.w - m1[3] - ((y.w - mu.w) * rs4.w) * m2[3]);
-    st_pair4<true>(hi, lo, off, o);
+    if (P.dy_fp16) {
+      o.x *= dscale; o.y *= dscale; o.z *= dscale; o.w *= dscale;
+      st_pair4<false>(hi, lo, off, o);
+    } else {
+      st_pair4<true>(hi, lo, off, o);
+    }
     if (P.dres != nullptr) {
       float* d = P.dres + (size_t)row * P.dres_ld + P.dres_coff + c;
       float4 v = dz;
@@ -929,6 +983,8 @@ extern "C" int coclr_bn_bwd(const coclr_bn_bwd_t* p, int num_sms, coclr_stream_t
   const dim3 grid(gx, ctiles);
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(p->sums, 0, sizeof(double) * 2 * p->C, s) != cudaSuccess) return COCLR_E_LAUNCH;
+  if (p->dy_fp16 && (!p->amax || !p->dy_scale)) return COCLR_E_ARG;
+  if (p->amax && cudaMemsetAsync(p->amax, 0, sizeof(float) * 2 * p->C, s) != cudaSuccess) return COCLR_E_LAUNCH;
   bn_bwd_reduce_kernel<<<grid, kColThreads, 0, s>>>(*p);
   bn_bwd_apply_kernel<<<grid, kColThreads, 0, s>>>(*p);
   return LAUNCH_OK();

@@ -402,7 +402,7 @@ class ParamStore:
 # ---------------------------------------------------------------------------------------------
 class _Act:
     __slots__ = ("spec", "dims", "data", "pl", "plw", "grad", "dy", "scale", "shift", "mean", "rstd", "ssum", "ssq", "idx",
-                 "bsums", "grad_written", "M")
+                 "bsums", "grad_written", "M", "dy_scale", "bamax")
 
 
 class Plan:
@@ -418,6 +418,10 @@ class Plan:
         self.graphs = {}        # captured CUDA graphs of the launch lists
         nsm = L.num_sms(dev)
         fnp, fbf, bnp = PRECISIONS[eng.precision]
+        # gradient planes: with fp16 forward planes dY is stored as fp16 hi/lo of dY * 2^k (k per tensor and step, chosen
+        # by coclr_bn_bwd from the data's range) so that the weight-gradient GEMM pairs it with the forward planes --
+        # tcgen05 kind::f16 wants one 16-bit format for both operands -- instead of a bf16 twin of every activation
+        gbf = 1 if fbf else 0
         # ---- activations ----
         acts = {}
         n_stat = sum(t.C for t in g.tensors if t.pending)
@@ -435,11 +439,8 @@ class Plan:
             if padded:
                 shape = (B,) + a.dims[:2] + (a.dims[2] + 2 * S2D_PAD, t.C)
             a.pl = ops.Planes(shape, fbf, dev, lo=fnp > 1, zero=padded)   # what every forward consumer reads
-            # bf16 twin for the weight-gradient GEMM (tcgen05 kind::f16 needs one format for both operands and
-            # the output gradients are bf16); not needed when the forward planes already are bf16
-            a.plw = (ops.Planes(shape, 1, dev, lo=bnp > 1, zero=padded) if (with_backward and not fbf)
-                     else (a.pl if with_backward else None))
-            a.data = a.grad = a.dy = a.idx = a.bsums = None
+            a.plw = a.pl if with_backward else None     # ... and the weight-gradient GEMM (same 16-bit format as dY)
+            a.data = a.grad = a.dy = a.idx = a.bsums = a.dy_scale = a.bamax = None
             a.grad_written = False
             if t.pending:
                 a.data = torch.empty(shape, dtype=torch.float32, device=dev)   # raw conv output (pre-BN)
@@ -455,7 +456,8 @@ class Plan:
             if with_backward and t is not g.input:
                 a.grad = torch.empty(shape, dtype=torch.float32, device=dev)
                 if t.pending:
-                    a.dy = ops.Planes(shape, 1, dev, lo=bnp > 1)
+                    a.dy = ops.Planes(shape, gbf, dev, lo=bnp > 1)
+                    a.dy_scale = torch.ones(2, dtype=torch.float32, device=dev)      # (s, 1/s) written by coclr_bn_bwd
             acts[t.index] = a
         self.acts = acts
         self.input = acts[g.input.index]
@@ -603,16 +605,25 @@ class Plan:
                 convs_into.setdefault(it.dst.index, []).append(it)
             elif kind == "pool":
                 pool_into[it.dst.index] = it
-        # reverse forward order: a tensor is handled at its BatchNorm / pool item, i.e. after every consumer
+        # reverse forward order: a tensor is handled at its BatchNorm / pool item, i.e. after every consumer.
+        # bwd_split: position in the list after which >= 75 % of the parameters have their final gradient -- the flat
+        # gradient is all-reduced in two parts, the first one while the rest of the backward pass still runs (the
+        # reference gets this overlap from DistributedDataParallel's bucketed reducer, main_nce.py:172)
+        total_params = sum(n for _, (o, n, _) in st.offsets.items())
+        done_params = sum(st.offsets[k][1] for k in ("2.weight", "2.bias", "4.weight", "4.bias") if k in st.offsets)
+        self.bwd_split, self.bwd_split_conv_off, self.bwd_split_bn_off = None, None, None
         for kind_r, it_r in reversed(g.items):
             if kind_r == "conv":
                 continue
+            if self.bwd_split is None and done_params >= 0.75 * total_params and len(bw) > 0:
+                self.bwd_split = len(bw)
             t = it_r if kind_r == "bn" else it_r.dst
             a = acts[t.index]
             if not a.grad_written:
                 raise RuntimeError("tensor %s never receives a gradient" % t.name)
             if t.pending:
                 a.bsums = torch.zeros(2 * t.C, dtype=torch.float64, device=dev)
+                a.bamax = torch.zeros(2 * t.C, dtype=torch.float32, device=dev)
                 first = t.bn_members[0][0]
                 goff = st.offsets[first + ".weight"][0]
                 boff_b = st.offsets[first + ".bias"][0]
@@ -624,10 +635,20 @@ class Plan:
                     res_args = (None, None, 0, 0, 0, None, 0, 0, 0)
                 bb = L.BnBwd(L.dptr(a.data), L.dptr(a.grad), t.C, 0, t.C, a.M, L.dptr(a.scale), L.dptr(a.shift),
                              L.dptr(a.mean), L.dptr(a.rstd), t.relu, L.dptr(a.bsums),
-                             L.dptr(st.grad[goff:]), L.dptr(st.grad[boff_b:]), L.dptr(a.dy.hi), L.dptr(a.dy.lo), *res_args)
+                             L.dptr(st.grad[goff:]), L.dptr(st.grad[boff_b:]), L.dptr(a.dy.hi), L.dptr(a.dy.lo), *res_args,
+                             0 if gbf else 1, L.dptr(a.bamax), L.dptr(a.dy_scale))
+                oscale = None if gbf else a.dy_scale[1:]
                 self.keep.append(bb)
                 bw.append((lib.coclr_bn_bwd, (C.byref(bb), nsm)))
+                if self.bwd_split is None:
+                    done_params += 2 * t.C
+                    self.bwd_split_bn_off = goff            # gammas of this tensor: first BN parameter done so far
                 for it in convs_into[t.index]:
+                    if self.bwd_split is None:
+                        names = [n + ".weight" for n in it.weight_names]
+                        done_params += sum(st.offsets[n][1] for n in names)
+                        off0 = st.offsets[names[0]][0]
+                        self.bwd_split_conv_off = off0 if self.bwd_split_conv_off is None else min(self.bwd_split_conv_off, off0)
                     sa = acts[it.src.index]
                     geom = ops.Geometry(it.k_eff, it.s_eff, it.p_eff)
                     dy = a.dy.src(it.dst_coff, _round8(it.cout), a.dims[0], a.dims[1], a.dims[2])
@@ -645,18 +666,18 @@ class Plan:
                         # the weight gradient is produced in the space-to-depth layout, then scattered back
                         dw_eff = eng.s2d[it.name]["dw_eff"]
                         wg = L.Wgrad(wsrc, geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin_eff,
-                                     L.dptr(dw_eff), bnp, 1, 1, splits)
+                                     L.dptr(dw_eff), bnp, gbf, gbf, splits, L.dptr(oscale))
                         self.keep += [wg, dy]
                         bw.append((eng._s2d_wgrad_op(it.name, wg), ()))
                     else:
                         wg = L.Wgrad(wsrc, geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin,
-                                     L.dptr(st.view_span([n + ".weight" for n in it.weight_names], grad=True)), bnp, 1, 1,
-                                     splits)
+                                     L.dptr(st.view_span([n + ".weight" for n in it.weight_names], grad=True)), bnp, gbf, gbf,
+                                     splits, L.dptr(oscale))
                         self.keep += [wg, dy]
                         bw.append((lib.coclr_conv_wgrad, (C.byref(wg),)))
                     if it.need_dgrad:
-                        dg = ops.make_conv(dy, 1, geom.c(1), B, sa.dims, eng.packed_bwd[it.name], sa.grad, it.src_coff,
-                                           accumulate=grad_seen(sa, it.src_coff, it.src_C), npass=bnp)
+                        dg = ops.make_conv(dy, gbf, geom.c(1), B, sa.dims, eng.packed_bwd[it.name], sa.grad, it.src_coff,
+                                           accumulate=grad_seen(sa, it.src_coff, it.src_C), npass=bnp, out_scale=oscale)
                         self.keep.append(dg)
                         bw.append((lib.coclr_conv_igemm, (C.byref(dg), nsm)))
             elif t.index in pool_into:
@@ -694,7 +715,7 @@ class EncoderEngine:
             self.packed_fwd[it.name] = pf
             self._packs.append((pf, w, False))
             if it.need_dgrad:
-                pb = ops.PackedWeights(it.cout, it.cin, taps, _round8(it.cout), 1, 1, dev)
+                pb = ops.PackedWeights(it.cout, it.cin, taps, _round8(it.cout), 1, 1 if fbf else 0, dev)   # format of dY
                 self.packed_bwd[it.name] = pb
                 self._packs.append((pb, w, True))
         if graph.head_dim is not None:
@@ -750,13 +771,33 @@ class EncoderEngine:
         op.__name__ = "coclr_conv_wgrad_s2d"
         return op
 
+    def _pack_table(self, backward):
+        """Device table for coclr_pack_weights_batch (built once per variant: the pointers never change)."""
+        key = bool(backward)
+        tabs = getattr(self, "_pack_tables", None)
+        if tabs is None:
+            tabs = self._pack_tables = {}
+        if key not in tabs:
+            entries = [(pw, w) for pw, w, is_bwd in self._packs if backward or not is_bwd]
+            arr = (L.Pack * len(entries))()
+            starts = [0]
+            for i, (pw, w) in enumerate(entries):
+                assert w.is_contiguous() and w.dtype == torch.float32
+                arr[i] = L.Pack(L.dptr(w), pw.Cout, pw.Cin, pw.taps, pw.cpad, pw.mode, pw.bf16,
+                                L.dptr(pw.wpk), L.dptr(pw.unscale))
+                starts.append(starts[-1] + pw.BN * pw.n_tiles)
+            dev = self.store.device
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev) if not L.DRY_RUN else None
+            rs = torch.tensor(starts, dtype=torch.int32, device=dev) if not L.DRY_RUN else None
+            tabs[key] = (raw, rs, len(entries), starts[-1])
+        return tabs[key]
+
     def pack_weights(self, backward=True):
-        """Re-derive the 16-bit hi/lo tile images from the current fp32 weights."""
+        """Re-derive the 16-bit hi/lo tile images from the current fp32 weights (one launch for all layers)."""
         self._refresh_s2d()
-        for pw, w, is_bwd in self._packs:
-            if is_bwd and not backward:
-                continue
-            pw.pack(w)
+        raw, rs, n, rows = self._pack_table(backward)
+        L.check(L.load().coclr_pack_weights_batch(L.dptr(raw), L.dptr(rs), n, rows, L.stream_ptr()),
+                "coclr_pack_weights_batch")
 
     def plan(self, B, T, H, W, training, with_backward):
         key = (B, T, H, W, bool(training), bool(with_backward))
@@ -907,10 +948,31 @@ class EncoderEngine:
             state[0].replay()
             L.LAUNCHES += state[1]
 
-    def backward(self, p, dq):
-        """dq: gradient w.r.t. the normalised features [B, dim]; accumulates into store.grad."""
+    def grad_ranges(self, p):
+        """[(lo, hi)] element ranges of the flat gradient that are final after the first backward segment, and the
+        complementary ranges (final at the end): conv weights, BatchNorm parameters and the head are three regions of
+        the flat buffer, each filled back to front by the backward pass."""
+        st = self.store
+        conv_end = min(o for k, (o, n, _) in st.offsets.items() if not k.endswith(".weight") or len(st.offsets[k][2]) == 1)
+        c0, b0 = p.bwd_split_conv_off, p.bwd_split_bn_off
+        first = [(c0, conv_end), (b0, st.numel)]
+        rest = [(0, c0), (conv_end, b0)]
+        return [r for r in first if r[1] > r[0]], [r for r in rest if r[1] > r[0]]
+
+    def backward(self, p, dq, mid_hook=None):
+        """dq: gradient w.r.t. the normalised features [B, dim]; accumulates into store.grad.  mid_hook (optional) is
+        called between the two segments of the launch list with the ranges of the flat gradient that are final."""
         p.dq.copy_(dq)
-        self._graphed(p, "bwd", lambda: self._run(p.bwd, side_fn=L.load().coclr_conv_wgrad))
+        wg = L.load().coclr_conv_wgrad
+        if mid_hook is None or p.bwd_split is None or p.bwd_split_conv_off is None or p.bwd_split_bn_off is None:
+            self._graphed(p, "bwd", lambda: self._run(p.bwd, side_fn=wg))
+            return False
+        first, rest = self.grad_ranges(p)
+        self._graphed(p, "bwd0", lambda: self._run(p.bwd[:p.bwd_split], side_fn=wg))
+        mid_hook(first)
+        self._graphed(p, "bwd1", lambda: self._run(p.bwd[p.bwd_split:], side_fn=wg))
+        mid_hook(rest)
+        return True
 
     def backbone_output_ncdhw(self, p):
         return p.backbone_out.pl.value().permute(0, 4, 1, 2, 3).contiguous()

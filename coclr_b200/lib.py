@@ -36,14 +36,15 @@ class Conv(C.Structure):
                 ("N", C.c_int), ("BN", C.c_int), ("n_tiles", C.c_int),
                 ("dst", C.c_void_p), ("dst_ld", C.c_int), ("dst_coff", C.c_int),
                 ("accumulate", C.c_int), ("stats_sum", C.c_void_p), ("stats_sq", C.c_void_p),
-                ("npass", C.c_int), ("a_bf16", C.c_int), ("b_bf16", C.c_int)]
+                ("npass", C.c_int), ("a_bf16", C.c_int), ("b_bf16", C.c_int), ("out_scale", C.c_void_p)]
 
 
 class Wgrad(C.Structure):
     _fields_ = [("src", Src), ("g", Geom), ("dy", Src),
                 ("B", C.c_int), ("Td", C.c_int), ("Hd", C.c_int), ("Wd", C.c_int),
                 ("Cout", C.c_int), ("Cin_real", C.c_int), ("dw", C.c_void_p),
-                ("npass", C.c_int), ("dy_bf16", C.c_int), ("src_bf16", C.c_int), ("splits", C.c_int)]
+                ("npass", C.c_int), ("dy_bf16", C.c_int), ("src_bf16", C.c_int), ("splits", C.c_int),
+                ("out_scale", C.c_void_p)]
 
 
 class Pack(C.Structure):
@@ -77,7 +78,7 @@ class BnBwd(C.Structure):
                 ("dy_hi", C.c_void_p), ("dy_lo", C.c_void_p),
                 ("res_hi", C.c_void_p), ("res_lo", C.c_void_p), ("res_ld", C.c_int), ("res_coff", C.c_int),
                 ("res_bf16", C.c_int), ("dres", C.c_void_p), ("dres_ld", C.c_int), ("dres_coff", C.c_int),
-                ("dres_accumulate", C.c_int)]
+                ("dres_accumulate", C.c_int), ("dy_fp16", C.c_int), ("amax", C.c_void_p), ("dy_scale", C.c_void_p)]
 
 
 class Pool(C.Structure):

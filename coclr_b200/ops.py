@@ -88,23 +88,25 @@ class PackedWeights:
 
 
 def make_conv(src, a_bf16, geom_c, B, dst_dims, pw, dst, dst_coff=0, accumulate=False, stats_sum=None,
-              stats_sq=None, npass=3):
+              stats_sq=None, npass=3, out_scale=None):
     Td, Hd, Wd = dst_dims
     return L.Conv(src, geom_c, B, Td, Hd, Wd, pw.Kreal, L.dptr(pw.wpk), L.dptr(pw.unscale),
                   pw.N, pw.BN, pw.n_tiles, L.dptr(dst), dst.shape[-1], dst_coff, int(bool(accumulate)),
-                  L.dptr(stats_sum), L.dptr(stats_sq), npass, int(a_bf16), pw.bf16)
+                  L.dptr(stats_sum), L.dptr(stats_sq), npass, int(a_bf16), pw.bf16, L.dptr(out_scale))
 
 
-def conv_igemm(src, a_bf16, geom_c, B, dst_dims, pw, dst, dst_coff=0, accumulate=False, stats=None, npass=3):
+def conv_igemm(src, a_bf16, geom_c, B, dst_dims, pw, dst, dst_coff=0, accumulate=False, stats=None, npass=3,
+               out_scale=None):
     """Run the implicit-GEMM conv. src: L.Src of 16-bit planes; dst: [B,Td,Hd,Wd,ld] fp32."""
     ssum = stats[:pw.N] if stats is not None else None
     ssq = stats[pw.N:] if stats is not None else None
-    p = make_conv(src, a_bf16, geom_c, B, dst_dims, pw, dst, dst_coff, accumulate, ssum, ssq, npass)
+    p = make_conv(src, a_bf16, geom_c, B, dst_dims, pw, dst, dst_coff, accumulate, ssum, ssq, npass, out_scale)
     L.check(L.load().coclr_conv_igemm(C.byref(p), L.num_sms(), L.stream_ptr()), "coclr_conv_igemm")
 
 
-def conv_wgrad(src, src_bf16, geom_c, dy_src, dy_bf16, B, dst_dims, Cout, Cin_real, dw, npass=3, splits=1):
+def conv_wgrad(src, src_bf16, geom_c, dy_src, dy_bf16, B, dst_dims, Cout, Cin_real, dw, npass=3, splits=1,
+               out_scale=None):
     Td, Hd, Wd = dst_dims
     p = L.Wgrad(src, geom_c, dy_src, B, Td, Hd, Wd, Cout, Cin_real, L.dptr(dw), npass, int(dy_bf16), int(src_bf16),
-                splits)
+                splits, L.dptr(out_scale))
     L.check(L.load().coclr_conv_wgrad(C.byref(p), L.stream_ptr()), "coclr_conv_wgrad")

@@ -70,6 +70,8 @@ typedef struct {
   int npass;         /* 1 = single 16-bit pass, 3 = hi/lo split (fp32-grade) */
   int a_bf16;        /* format of the src planes: 0 = fp16, 1 = bf16 */
   int b_bf16;        /* format of the packed weights */
+  const float* out_scale; /* device scalar multiplied into the result (e.g. 1/s of gradient planes stored scaled by s, see
+                           * coclr_bn_bwd_t.dy_scale), or NULL */
 } coclr_conv_t;
 int coclr_conv_igemm(const coclr_conv_t* p, int num_sms, coclr_stream_t stream);
 size_t coclr_conv_packed_bytes(int N, int Kreal, int* BN_out, int* n_tiles_out);
@@ -96,6 +98,7 @@ typedef struct {
   int npass;
   int dy_bf16, src_bf16;
   int splits;        /* pixel-range splits (>= 1) */
+  const float* out_scale; /* device scalar multiplied into the result before it is added to dw, or NULL */
 } coclr_wgrad_t;
 int coclr_conv_wgrad(const coclr_wgrad_t* p, coclr_stream_t stream);
 
@@ -113,6 +116,10 @@ typedef struct {
   float* unscale; /* [n_tiles*BN] */
 } coclr_pack_t;
 int coclr_pack_weights(const coclr_pack_t* p, coclr_stream_t stream);
+/* every weight of an encoder in one launch: table_dev = device array of n coclr_pack_t, row_start_dev = device int
+ * [n + 1], first packed row (of the n_tiles*BN rows coclr_conv_packed_bytes implies) of each entry, ascending */
+int coclr_pack_weights_batch(const coclr_pack_t* table_dev, const int* row_start_dev, int n, int total_rows,
+                             coclr_stream_t stream);
 
 /* ---- BatchNorm3d statistics -> affine (train mode; backbone/s3dg.py:16,46-47) ------------------
  * per-channel sums written by coclr_conv_igemm -> (scale, shift), saved (mean, rstd) for backward, running-stat
@@ -191,6 +198,15 @@ typedef struct {
   int res_ld, res_coff, res_bf16;
   float* dres; /* fp32 [M, dres_ld] at dres_coff, or NULL */
   int dres_ld, dres_coff, dres_accumulate;
+  /* dy_fp16 != 0: the planes are written as fp16 hi/lo of dY * s, s a power of two chosen per call so that the largest
+   * |dY| the data allows (a per-channel bound from max |dz|, max |xhat| and the two means, reduced over the channels)
+   * lands at 2^14: ~22 significant bits near the top of the range instead of bf16 hi/lo's 16, and the weight-gradient
+   * GEMM can pair them with the forward pass's fp16 activation planes (tcgen05 kind::f16 needs one format for both
+   * operands) -- no bf16 twin of every activation.  dy_scale[0] = s, dy_scale[1] = 1/s (device, written by the call;
+   * consumers pass &dy_scale[1] as out_scale).  amax: workspace [2*C] floats. */
+  int dy_fp16;
+  float* amax;
+  float* dy_scale;
 } coclr_bn_bwd_t;
 int coclr_bn_bwd(const coclr_bn_bwd_t* p, int num_sms, coclr_stream_t stream);
 

@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+LOG=gpurun_out/r2_dbg.log
+: > $LOG
+for dbg in 0 1 2 3 4; do
+  export COCLR_TMA_DBG=$dbg
+  echo "---- DBG=$dbg" >> $LOG
+  timeout 120 python tests/tools/run_one_conv.py s2d 3 64 1 4 4 32 32 64 64 >> $LOG 2>&1
+  STRIDE=2,1,1 timeout 120 python tests/tools/run_one_conv.py fwd 64 64 7 1 1 32 32 64 64 >> $LOG 2>&1
+  timeout 120 python tests/tools/run_one_conv.py fwd 64 192 1 3 3 32 16 32 32 >> $LOG 2>&1
+  timeout 120 python tests/tools/run_one_conv.py dgrad 64 192 1 3 3 32 16 32 32 >> $LOG 2>&1
+done
+cat $LOG

@@ -280,3 +280,53 @@ def test_fused_bn_finalize_apply_split(training, diag):
     assert _rel(rm, rm_ref) < 1e-6 and _rel(rv, rv_ref) < 1e-6
     if training:
         assert _rel(mean, xs.mean(0)) < 1e-6
+
+
+@pytest.mark.parametrize("fp16", [1, 0], ids=["fp16_scaled", "bf16"])
+@pytest.mark.parametrize("C,M,spread", [(64, 4096, 1.0), (24, 777, 1e-4), (192, 2048, 1e3)])
+def test_bn_relu_backward_planes(fp16, C, M, spread, diag):
+    """coclr_bn_bwd against autograd of relu(batch_norm(y)) in float64 (NativeBatchNormBackward0 + ReluBackward0 of the
+    reference's graph): dgamma / dbeta and the dY operand planes -- bf16 hi/lo, or fp16 hi/lo of dY * s with the
+    power-of-two s the kernel derives from the data (dy_scale), for gradient magnitudes from 1e-4 to 1e3 (`spread`)
+    and channels of very different scale inside one tensor."""
+    import ctypes as C_
+    from coclr_b200 import ops, lib as L
+    g = torch.Generator(device="cuda").manual_seed(C + M)
+    y = torch.randn(M, C, device="cuda", generator=g) * 1.5 + 0.3
+    gamma = torch.rand(C, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C, device="cuda", generator=g) * 0.2
+    chan = torch.logspace(-3, 0, C, device="cuda")                      # per-channel gradient magnitudes over 3 decades
+    dA = torch.randn(M, C, device="cuda", generator=g) * chan * spread
+    yd = y.double().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    out = torch.relu(F.batch_norm(yd, None, None, gd, bd, True, 0.1, 1e-5))
+    ref_dy, ref_dg, ref_db = torch.autograd.grad(out, [yd, gd, bd], dA.double())
+    mean = y.double().mean(0)
+    var = y.double().var(0, unbiased=False)
+    rstd = (var + 1e-5).rsqrt()
+    scale = (gamma.double() * rstd).float()
+    shift = (beta.double() - mean * gamma.double() * rstd).float()
+    sums = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    amax = torch.zeros(2 * C, device="cuda")
+    dscale = torch.ones(2, device="cuda")
+    dgam, dbet = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    pl = ops.Planes((M, C), 0 if fp16 else 1, "cuda")
+    bb = L.BnBwd(L.dptr(y), L.dptr(dA), C, 0, C, M, L.dptr(scale), L.dptr(shift), L.dptr(mean.float()), L.dptr(rstd.float()),
+                 1, L.dptr(sums), L.dptr(dgam), L.dptr(dbet), L.dptr(pl.hi), L.dptr(pl.lo),
+                 None, None, 0, 0, 0, None, 0, 0, 0, fp16, L.dptr(amax), L.dptr(dscale))
+    L.check(L.load().coclr_bn_bwd(C_.byref(bb), L.num_sms(), L.stream_ptr()), "coclr_bn_bwd")
+    torch.cuda.synchronize()
+    got = pl.value().double() * (float(dscale[1]) if fp16 else 1.0)
+    e_dy = _rel(got, ref_dy)
+    # per-channel error relative to that channel's own scale: small channels must not drown in the tensor-wide scale
+    per_c = ((got - ref_dy).abs().amax(0) / ref_dy.abs().amax(0).clamp_min(1e-300)).max()
+    diag["bn_bwd/fp16%d_C%d_s%g" % (fp16, C, spread)] = [e_dy, float(per_c), float(dscale[0])]
+    assert _rel(dgam, ref_dg) < 1e-4 and _rel(dbet, ref_db) < 1e-4
+    if fp16:
+        s = float(dscale[0])
+        assert s > 0 and abs(np.log2(s) - round(np.log2(s))) < 1e-6          # a power of two
+        top = float(pl.value().abs().max())
+        assert 2.0 ** 8 < top <= 2.0 ** 14, top                                # the range bound is not wildly pessimistic
+        assert e_dy < 2e-6 and float(per_c) < 2e-5, (e_dy, float(per_c))
+    else:
+        assert e_dy < 3e-5

@@ -386,3 +386,51 @@ def test_reference_adam_state_converts_to_flat(tmp_path):
         assert not main_nce.load_optimizer_state(opt, {"state": {}, "param_groups": []}, enc, "cpu")
     finally:
         L.DRY_RUN = False
+
+
+def test_overlapped_allreduce_ranges_are_final_when_reduced():
+    """The flat gradient is all-reduced in two parts (moco._EncodeFn.backward): the first part while the second segment
+    of the backward launch list still runs.  Host logic, checked on the dry-run plan: the two range sets partition the
+    buffer, and no launch of the second segment writes a gradient that the first all-reduce has already taken."""
+    import ctypes as C
+    from coclr_b200 import lib as L, engine as E
+    from coclr_b200.s3d_spec import s3d_stages
+    from coclr_b200.r50_spec import r50_stages
+    L.DRY_RUN = True
+    try:
+        for stages, fs in ((s3d_stages(3), 1024), (r50_stages(3), 2048)):
+            g = E.Graph(stages, 3, head_dim=128, feature_size=fs, bb_prefix="0.")
+            st = E.ParamStore(g, "cpu")
+            eng = E.EncoderEngine(st, g, "parity")
+            p = eng.plan(2, 8, 64, 64, True, True)
+            assert p.bwd_split is not None and 0 < p.bwd_split < len(p.bwd)
+            first, rest = eng.grad_ranges(p)
+            cover = sorted(first + rest)
+            assert cover[0][0] == 0 and cover[-1][1] == st.numel
+            assert all(a[1] == b[0] for a, b in zip(cover, cover[1:])), cover
+            assert sum(hi - lo for lo, hi in first) >= 0.7 * st.numel
+            base = st.grad.data_ptr()
+
+            def written(fn, args):
+                """element offsets of the flat gradient this launch writes"""
+                o = args[0]._obj if (args and hasattr(args[0], "_obj")) else None
+                name = fn.__name__
+                out = []
+                if name == "coclr_conv_wgrad":
+                    out.append(o.dw)
+                elif name == "coclr_conv_wgrad_s2d":
+                    out.append(eng.s2d[[k for k in eng.s2d][0]]["dw"].data_ptr())
+                elif name == "coclr_bn_bwd":
+                    out += [o.dgamma, o.dbeta]
+                elif name == "coclr_l2norm_bwd":
+                    out.append(args[4].value)
+                elif name == "coclr_bias_relu_bwd":
+                    out.append(args[3].value)
+                return [(ptr - base) // 4 for ptr in out if ptr]
+            late = [off for fn, args in p.bwd[p.bwd_split:] for off in written(fn, args)]
+            early = [off for fn, args in p.bwd[:p.bwd_split] for off in written(fn, args)]
+            assert late and early
+            assert all(any(lo <= off < hi for lo, hi in rest) for off in late), "a late launch writes an early range"
+            assert all(any(lo <= off < hi for lo, hi in first) for off in early), "an early launch writes a late range"
+    finally:
+        L.DRY_RUN = False
