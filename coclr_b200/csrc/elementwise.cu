@@ -2,6 +2,8 @@
 // global average pooling, input packing, L2-normalise, momentum (EMA) update, queue enqueue, Adam.
 // Activations are channels-last rows; channel counts are multiples of 8 for the 16-bit planes and every
 // kernel moves 8-16 bytes per thread with consecutive threads on consecutive addresses.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "coclr_b200.h"
 

@@ -306,12 +306,13 @@ def test_bn_relu_backward_planes(fp16, C, M, spread, diag):
     rstd = (var + 1e-5).rsqrt()
     scale = (gamma.double() * rstd).float()
     shift = (beta.double() - mean * gamma.double() * rstd).float()
+    mean32, rstd32 = mean.float().contiguous(), rstd.float().contiguous()    # keep alive: the kernel gets raw pointers
     sums = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
     amax = torch.zeros(2 * C, device="cuda")
     dscale = torch.ones(2, device="cuda")
     dgam, dbet = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     pl = ops.Planes((M, C), 0 if fp16 else 1, "cuda")
-    bb = L.BnBwd(L.dptr(y), L.dptr(dA), C, 0, C, M, L.dptr(scale), L.dptr(shift), L.dptr(mean.float()), L.dptr(rstd.float()),
+    bb = L.BnBwd(L.dptr(y), L.dptr(dA), C, 0, C, M, L.dptr(scale), L.dptr(shift), L.dptr(mean32), L.dptr(rstd32),
                  1, L.dptr(sums), L.dptr(dgam), L.dptr(dbet), L.dptr(pl.hi), L.dptr(pl.lo),
                  None, None, 0, 0, 0, None, 0, 0, 0, fp16, L.dptr(amax), L.dptr(dscale))
     L.check(L.load().coclr_bn_bwd(C_.byref(bb), L.num_sms(), L.stream_ptr()), "coclr_bn_bwd")
