@@ -41,10 +41,14 @@ struct TmaTile {
   int idx[4];
   int n_tile;
 };
-COCLR_DEVINL TmaTile tma_decode(const TmaPlan& L, int tile) {
+// Work item -> tile.  Items enumerate (pixel tile, N tile) with the N tile fastest; in pair mode an item is a PAIR of
+// consecutive pixel tiles (one per CTA of the cluster).  A pixel-tile number past the end (the odd tile out of a pair)
+// decodes to a batch index past the tensor: its loads are zero-filled, its stores clipped, its rows invalid.
+COCLR_DEVINL TmaTile tma_decode(const TmaPlan& L, int item, int pair, int rank) {
   TmaTile t;
-  t.n_tile = tile % L.n_tiles_n;
-  int m = tile / L.n_tiles_n;
+  t.n_tile = item % L.n_tiles_n;
+  int m = item / L.n_tiles_n;
+  if (pair) m = 2 * m + rank;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     t.idx[d] = m % L.ntiles[d];
@@ -54,10 +58,19 @@ COCLR_DEVINL TmaTile tma_decode(const TmaPlan& L, int tile) {
   return t;
 }
 
-template <int kNPass>
+// kPair: the kernel runs as clusters of two CTAs that execute ONE tcgen05.mma.cta_group::2 stream (issued by the rank-0
+// CTA) over M = 256 pixels -- 128 per CTA, each in its own shared memory and tensor memory -- against a weight tile that
+// is SPLIT between the two CTAs (each holds half of its rows): per CTA and MMA the weight bytes read from shared memory
+// and fetched from L2 halve, and one instruction does the work of two.  Both matter here: M=128 x N<=192 instructions
+// are bound by shared-memory operand bandwidth (and a ~110-cycle per-instruction floor for N <= 64), not by the tensor
+// pipe.  Synchronisation: loads of both CTAs complete on the rank-0 CTA's "full" barriers
+// (cp.async.bulk.tensor.cta_group::2 may signal the peer's mbarrier); tcgen05.commit multicasts the "empty" / "tile done"
+// arrivals to both CTAs; the epilogue warps of both CTAs arrive on rank 0's accumulator-free barrier.
+template <int kNPass, bool kPair>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     conv_tma_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-                    const __grid_constant__ CUtensorMap map_out, const __grid_constant__ TmaArgs P) {
+                    const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ TmaArgs P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr bool kLo = kNPass > 1;
@@ -78,27 +91,35 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const uint32_t ncta = kPair ? 2u : 1u;
+  const int first_item = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_items = kPair ? L.pair_items : L.total_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTmaMaxASlots; ++s) {
-      mbar_init(&a_full[s], 1);
+      mbar_init(&a_full[s], ncta);     // one arrive.expect_tx per loading CTA
       mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < kTmaMaxBSlots; ++s) {
-      mbar_init(&b_full[s], 1);
+      mbar_init(&b_full[s], ncta);
       mbar_init(&b_empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&t_full[a], 1);
-      mbar_init(&t_empty[a], 4);
+      mbar_init(&t_empty[a], 4 * ncta);
     }
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < 256; i += kTmaThreads)
     unscale_tab[i] = 1.f;  // per tile the epilogue reads n_tile*BN + c; filled below when there is a table
-  if (warp == 5) tmem_alloc<512>(tmem_holder);
+  if (warp == 5) {
+    if constexpr (kPair) tmem_alloc_2cta<512>(tmem_holder); else tmem_alloc<512>(tmem_holder);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);   // warp-uniform for the compiler
 
@@ -108,55 +129,112 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       tma_prefetch_desc(&map_hi);
       if (kLo) tma_prefetch_desc(&map_lo);
       uint32_t slot = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < L.total_tiles; tile += gridDim.x) {
-        const TmaTile t = tma_decode(L, tile);
+      for (int item = first_item; item < n_items; item += item_stride) {
+        const TmaTile t = tma_decode(L, item, kPair, (int)rank);
         const int ty0 = L.sel_dim >= 0 ? t.idx[L.sel_dim] : 0;
         const int ty1 = L.sel_dim >= 0 ? ty0 + 1 : L.n_types;
         for (int cc = 0; cc < L.nc; ++cc) {
           for (int ty = ty0; ty < ty1; ++ty) {
             const TmaSlabType& S = L.type[ty];
             mbar_wait(&a_empty[slot], phase ^ 1u);
-            mbar_arrive_expect_tx(&a_full[slot], kPlanes * (uint32_t)L.slab_bytes);
             const int c0 = cc * L.a_c0_step;
             const int c1 = t.idx[0] * L.a_mul[0] + S.d[0];
             const int c2 = t.idx[1] * L.a_mul[1] + S.d[1];
             const int c3 = t.idx[2] * L.a_mul[2] + S.d[2];
             const int c4 = t.idx[3] * L.a_mul[3] + S.d[3];
             const uint32_t dst = a_base + slot * (uint32_t)L.a_slot_bytes;
-            tma_load_5d(dst, &map_hi, &a_full[slot], c0, c1, c2, c3, c4);
-            if (kLo) tma_load_5d(dst + (uint32_t)L.plane_stride, &map_lo, &a_full[slot], c0, c1, c2, c3, c4);
+            if constexpr (kPair) {
+              const uint32_t bar = mapa_rank0(smem_u32(&a_full[slot]));
+              mbar_arrive_expect_tx_cluster(bar, kPlanes * (uint32_t)L.slab_bytes);
+              tma_load_5d_2cta(dst, &map_hi, bar, c0, c1, c2, c3, c4);
+              if (kLo) tma_load_5d_2cta(dst + (uint32_t)L.plane_stride, &map_lo, bar, c0, c1, c2, c3, c4);
+            } else {
+              mbar_arrive_expect_tx(&a_full[slot], kPlanes * (uint32_t)L.slab_bytes);
+              tma_load_5d(dst, &map_hi, &a_full[slot], c0, c1, c2, c3, c4);
+              if (kLo) tma_load_5d(dst + (uint32_t)L.plane_stride, &map_lo, &a_full[slot], c0, c1, c2, c3, c4);
+            }
             if (++slot == (uint32_t)L.a_slots) { slot = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 5) {
-    // ===================== weight loader (bulk copies of pre-swizzled tile images) =====================
+    // ===================== weight loader =====================
     if (elect_one()) {
-      const uint32_t tile_bytes = kPlanes * (uint32_t)L.BN * 128u;          // what one K chunk needs in smem
-      const size_t img_stride = (size_t)2u * (size_t)L.BN * 128u;            // packed image: hi and lo of every chunk
-      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(P.wpk);
-      if (L.b_resident) {
-        // the whole [nkc] image of the (single) N tile, once
-        mbar_arrive_expect_tx(&b_full[0], (uint32_t)L.nkc * tile_bytes);
-        for (int kc = 0; kc < L.nkc; ++kc)
-          bulk_g2s(smem + L.off_b + (size_t)kc * tile_bytes, wbase + (size_t)kc * img_stride, tile_bytes, &b_full[0]);
+      if constexpr (kPair) {
+        // Tensor-map loads of BN/2-row boxes of the pre-swizzled packed image (rows of 128 bytes: hi rows of a K chunk,
+        // then its lo rows).  Plain 3-pass mode: this CTA's half of the hi rows and of the lo rows.  Stacked mode
+        // (see the MMA issuer): region Y (BN rows) = ALL hi rows on rank 0 / ALL lo rows on rank 1 -- the two halves of the
+        // N = 2*BN operand of a_hi x [b_hi; b_lo] -- and region X (BN/2 rows) = this CTA's half of the hi rows for
+        // a_lo x b_hi.
+        tma_prefetch_desc(&map_w);
+        const uint32_t half_bytes = (uint32_t)(L.BN / 2) * 128u;
+        const uint32_t step_bytes = (uint32_t)L.b_tile_bytes;
+        const bool stacked = kLo && L.stacked;
+        auto load_step = [&](uint32_t dst, uint32_t bar, int n_tile, int kc) {
+          const int row0 = (n_tile * L.nkc + kc) * 2 * L.BN;      // hi rows [row0, +BN), lo rows [row0 + BN, +BN)
+          const int h = L.BN / 2;
+          if (stacked) {
+            const int y0 = row0 + (int)rank * L.BN;                 // rank 0: hi plane, rank 1: lo plane
+            tma_load_2d_2cta(dst, &map_w, bar, 0, y0);
+            tma_load_2d_2cta(dst + half_bytes, &map_w, bar, 0, y0 + h);
+            tma_load_2d_2cta(dst + 2u * half_bytes, &map_w, bar, 0, row0 + (int)rank * h);
+          } else {
+            tma_load_2d_2cta(dst, &map_w, bar, 0, row0 + (int)rank * h);
+            if (kLo) tma_load_2d_2cta(dst + half_bytes, &map_w, bar, 0, row0 + L.BN + (int)rank * h);
+          }
+        };
+        if (L.b_resident) {
+          const uint32_t bar = mapa_rank0(smem_u32(&b_full[0]));
+          mbar_arrive_expect_tx_cluster(bar, (uint32_t)L.nkc * step_bytes);
+          for (int kc = 0; kc < L.nkc; ++kc) load_step(b_base + (uint32_t)kc * step_bytes, bar, 0, kc);
+        } else {
+          uint32_t slot = 0, phase = 0;
+          for (int item = first_item; item < n_items; item += item_stride) {
+            const TmaTile t = tma_decode(L, item, kPair, (int)rank);
+            const int ty0 = L.sel_dim >= 0 ? t.idx[L.sel_dim] : 0;
+            const int ty1 = L.sel_dim >= 0 ? ty0 + 1 : L.n_types;
+            for (int cc = 0; cc < L.nc; ++cc) {
+              for (int ty = ty0; ty < ty1; ++ty) {
+                const TmaSlabType& S = L.type[ty];
+                for (int j = 0; j < S.nshift; ++j) {
+                  mbar_wait(&b_empty[slot], phase ^ 1u);
+                  const uint32_t bar = mapa_rank0(smem_u32(&b_full[slot]));
+                  mbar_arrive_expect_tx_cluster(bar, step_bytes);
+                  load_step(b_base + slot * step_bytes, bar, t.n_tile, S.tap[j] * L.nc + cc);
+                  if (++slot == (uint32_t)L.b_slots) { slot = 0; phase ^= 1u; }
+                }
+              }
+            }
+          }
+        }
       } else {
-        uint32_t slot = 0, phase = 0;
-        for (int tile = blockIdx.x; tile < L.total_tiles; tile += gridDim.x) {
-          const TmaTile t = tma_decode(L, tile);
-          const int ty0 = L.sel_dim >= 0 ? t.idx[L.sel_dim] : 0;
-          const int ty1 = L.sel_dim >= 0 ? ty0 + 1 : L.n_types;
-          for (int cc = 0; cc < L.nc; ++cc) {
-            for (int ty = ty0; ty < ty1; ++ty) {
-              const TmaSlabType& S = L.type[ty];
-              for (int j = 0; j < S.nshift; ++j) {
-                const int kc = S.tap[j] * L.nc + cc;
-                mbar_wait(&b_empty[slot], phase ^ 1u);
-                mbar_arrive_expect_tx(&b_full[slot], tile_bytes);
-                bulk_g2s(smem + L.off_b + (size_t)slot * tile_bytes,
-                         wbase + ((size_t)t.n_tile * L.nkc + kc) * img_stride, tile_bytes, &b_full[slot]);
-                if (++slot == (uint32_t)L.b_slots) { slot = 0; phase ^= 1u; }
+        // bulk copies of pre-swizzled tile images
+        const uint32_t tile_bytes = kPlanes * (uint32_t)L.BN * 128u;          // what one K chunk needs in smem
+        const size_t img_stride = (size_t)2u * (size_t)L.BN * 128u;            // packed image: hi and lo of every chunk
+        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(P.wpk);
+        if (L.b_resident) {
+          // the whole [nkc] image of the (single) N tile, once
+          mbar_arrive_expect_tx(&b_full[0], (uint32_t)L.nkc * tile_bytes);
+          for (int kc = 0; kc < L.nkc; ++kc)
+            bulk_g2s(smem + L.off_b + (size_t)kc * tile_bytes, wbase + (size_t)kc * img_stride, tile_bytes, &b_full[0]);
+        } else {
+          uint32_t slot = 0, phase = 0;
+          for (int item = first_item; item < n_items; item += item_stride) {
+            const TmaTile t = tma_decode(L, item, kPair, (int)rank);
+            const int ty0 = L.sel_dim >= 0 ? t.idx[L.sel_dim] : 0;
+            const int ty1 = L.sel_dim >= 0 ? ty0 + 1 : L.n_types;
+            for (int cc = 0; cc < L.nc; ++cc) {
+              for (int ty = ty0; ty < ty1; ++ty) {
+                const TmaSlabType& S = L.type[ty];
+                for (int j = 0; j < S.nshift; ++j) {
+                  const int kc = S.tap[j] * L.nc + cc;
+                  mbar_wait(&b_empty[slot], phase ^ 1u);
+                  mbar_arrive_expect_tx(&b_full[slot], tile_bytes);
+                  bulk_g2s(smem + L.off_b + (size_t)slot * tile_bytes,
+                           wbase + ((size_t)t.n_tile * L.nkc + kc) * img_stride, tile_bytes, &b_full[slot]);
+                  if (++slot == (uint32_t)L.b_slots) { slot = 0; phase ^= 1u; }
+                }
               }
             }
           }
@@ -164,24 +242,27 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       }
     }
   } else if (warp == 6) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc(P.a_bf16 ? 1u : 0u, P.b_bf16 ? 1u : 0u, 0u, 0u, 128u, (uint32_t)L.BN);
+    // ===================== MMA issuer (rank 0 only in pair mode) =====================
+    if (!kPair || rank == 0) {
+    const uint32_t mma_m = kPair ? 256u : 128u;
+    const uint32_t idesc = make_idesc(P.a_bf16 ? 1u : 0u, P.b_bf16 ? 1u : 0u, 0u, 0u, mma_m, (uint32_t)L.BN);
     // stacked mode (narrow layers): the hi rows and the lo rows of a weight tile are adjacent in shared memory, so
     // a_hi x [b_hi; b_lo] is ONE instruction with N = 2*BN whose second half of the accumulator collects a_hi*b_lo;
     // with a_lo x b_hi that is 2 instructions per K step instead of 3, and a third less operand traffic from shared
     // memory -- which, not the tensor pipe, bounds M=128 x N<=128 instructions (A 4 KB + B 32*N bytes per 16-deep step
     // against 128 B/clk).  The epilogue adds the two halves.
-    const uint32_t idesc2 = make_idesc(P.a_bf16 ? 1u : 0u, P.b_bf16 ? 1u : 0u, 0u, 0u, 128u, 2u * (uint32_t)L.BN);
+    const uint32_t idesc2 = make_idesc(P.a_bf16 ? 1u : 0u, P.b_bf16 ? 1u : 0u, 0u, 0u, mma_m, 2u * (uint32_t)L.BN);
     const bool stacked = kLo && L.stacked;
-    const uint32_t tile_bytes = kPlanes * (uint32_t)L.BN * 128u;
-    const uint32_t b_lo_off = (uint32_t)L.BN * 128u;
+    const uint32_t tile_bytes = (uint32_t)L.b_tile_bytes;
+    // offset of the second weight region of a step: lo rows (plain), or region X of the stacked pair layout
+    const uint32_t b_second = kPair ? (stacked ? (uint32_t)L.BN * 128u : (uint32_t)(L.BN / 2) * 128u) : (uint32_t)L.BN * 128u;
     uint32_t aslot = 0, aphase = 0, bslot = 0, bphase = 0, it = 0;
     if (L.b_resident) {
       mbar_wait_spin(&b_full[0], 0);
       tc_fence_after();
     }
-    for (int tile = blockIdx.x; tile < L.total_tiles; tile += gridDim.x, ++it) {
-      const TmaTile t = tma_decode(L, tile);
+    for (int item = first_item; item < n_items; item += item_stride, ++it) {
+      const TmaTile t = tma_decode(L, item, kPair, 0);
       const int ty0 = L.sel_dim >= 0 ? t.idx[L.sel_dim] : 0;
       const int ty1 = L.sel_dim >= 0 ? ty0 + 1 : L.n_types;
       const uint32_t acc = it & 1u;
@@ -204,31 +285,38 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
               tc_fence_after();
               sb = b_base + bslot * tile_bytes;
             }
-            if (elect_one()) {
+            if (elect_one() && !(L.dbg & 8)) {
               const uint32_t sa = sa0 + (uint32_t)j * (uint32_t)L.shift_bytes;
               const uint64_t a_hi = make_smem_desc(sa, 16, 1024);
               const uint64_t b_hi = make_smem_desc(sb, 16, 1024);
               if constexpr (kLo) {
                 const uint64_t a_lo = make_smem_desc(sa + (uint32_t)L.plane_stride, 16, 1024);
-                const uint64_t b_lo = make_smem_desc(sb + b_lo_off, 16, 1024);
+                const uint64_t b_2 = make_smem_desc(sb + b_second, 16, 1024);
                 if (stacked) {
+                  // pair mode: b_hi points at region Y (N = 2*BN over the pair), b_2 at region X (this CTA's hi half)
+                  const uint64_t b_x = kPair ? b_2 : b_hi;
 #pragma unroll
-                  for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc2, (started | k) != 0);
+                  for (uint32_t k = 0; k < 4; ++k)
+                    umma_f16_t<kPair>(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc2, (started | k) != 0);
 #pragma unroll
-                  for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                  for (uint32_t k = 0; k < 4; ++k) umma_f16_t<kPair>(tmem_d, a_lo + 2 * k, b_x + 2 * k, idesc, 1u);
                 } else {
 #pragma unroll
-                for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, (started | k) != 0);
+                  for (uint32_t k = 0; k < 4; ++k)
+                    umma_f16_t<kPair>(tmem_d, a_hi + 2 * k, b_2 + 2 * k, idesc, (started | k) != 0);
 #pragma unroll
-                for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                  for (uint32_t k = 0; k < 4; ++k) umma_f16_t<kPair>(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
 #pragma unroll
-                for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                  for (uint32_t k = 0; k < 4; ++k) umma_f16_t<kPair>(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
                 }
               } else {
 #pragma unroll
-                for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (started | k) != 0);
+                for (uint32_t k = 0; k < 4; ++k)
+                  umma_f16_t<kPair>(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (started | k) != 0);
               }
-              if (!L.b_resident) umma_commit(&b_empty[bslot]);
+              if (!L.b_resident) umma_commit_t<kPair>(&b_empty[bslot]);
+            } else if ((L.dbg & 8) && !L.b_resident && elect_one()) {
+              umma_commit_t<kPair>(&b_empty[bslot]);
             }
             started = 1u;
             __syncwarp();
@@ -236,13 +324,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
               if (++bslot == (uint32_t)L.b_slots) { bslot = 0; bphase ^= 1u; }
             }
           }
-          if (elect_one()) umma_commit(&a_empty[aslot]);   // the slab may be overwritten once these MMAs have read it
+          if (elect_one()) umma_commit_t<kPair>(&a_empty[aslot]);   // the slab may be overwritten once these MMAs have read it
           __syncwarp();
           if (++aslot == (uint32_t)L.a_slots) { aslot = 0; aphase ^= 1u; }
         }
       }
-      if (elect_one()) umma_commit(&t_full[acc]);
+      if (elect_one()) umma_commit_t<kPair>(&t_full[acc]);
       __syncwarp();
+    }
     }
   } else {
     // ===================== epilogue (warps 0-3) =====================
@@ -272,8 +361,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       ri[3] = r;
     }
     uint32_t it = 0, nstore = 0;
-    for (int tile = blockIdx.x; tile < L.total_tiles; tile += gridDim.x, ++it) {
-      const TmaTile t = tma_decode(L, tile);
+    for (int item = first_item; item < n_items; item += item_stride, ++it) {
+      const TmaTile t = tma_decode(L, item, kPair, (int)rank);
       const uint32_t acc = it & 1u;
       bool valid = true;
       int oc[4];
@@ -331,7 +420,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           }
           ++nstore;
           if (want_stats && !(L.dbg & 2)) {
-            // lane c sums column c over the warp's valid rows, reading the swizzled block back (conflict-free)
+            // lane c sums column c over the warp's valid rows, reading the swizzled block back (conflict-free; a variant
+            // with 16-byte reads + shuffle reduction measured slower)
             float a = 0.f, b = 0.f;
             const uint32_t cchunk = (uint32_t)lane >> 2, cword = ((uint32_t)lane & 3u) << 2;
 #pragma unroll 8
@@ -349,7 +439,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (leader) mbar_arrive(&t_empty[acc]);
+      if (leader) {
+        if constexpr (kPair) mbar_arrive_cluster(mapa_rank0(smem_u32(&t_empty[acc])));
+        else mbar_arrive(&t_empty[acc]);
+      }
       if (want_stats && L.n_tiles_n > 1) {
 #pragma unroll
         for (int kq = 0; kq < 8; ++kq) {
@@ -391,10 +484,11 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // the peer may still be signalling this CTA's barriers / reading its smem
   if (warp == 5) {
     tc_fence_after();
     __syncwarp();
-    tmem_dealloc<512>(tmem_base);
+    if constexpr (kPair) tmem_dealloc_2cta<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -427,7 +521,7 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static bool encode_map(CUtensorMap* m, const MapSpec& s, int which) {
+static bool encode_map(CUtensorMap* m, const MapSpec& s, int which, int rank = 5, bool swizzle = true) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[5], strides[4];
@@ -439,8 +533,9 @@ static bool encode_map(CUtensorMap* m, const MapSpec& s, int which) {
   }
   for (int i = 0; i < 4; ++i) strides[i] = s.strides[i];
   const CUtensorMapDataType dt = s.elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
-  CUresult r = fn(m, dt, 5, s.base[which], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(m, dt, rank, s.base[which], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (getenv("COCLR_TMA_DEBUG")) fprintf(stderr, "coclr: cuTensorMapEncodeTiled failed (%d)\n", (int)r);
     return false;
@@ -694,16 +789,27 @@ static bool conv_tma_plan_variant(const coclr_conv_t& P, int variant, TmaPlan& L
   if (((uintptr_t)O.base[0] & 15) || (old4 % 16) != 0 || (ld2 % 16) != 0) return false;
   for (int d = 0; d < 5; ++d)
     if (A.box[d] > 256 || O.box[d] > 256 || A.dims[d] == 0 || O.dims[d] == 0) return false;
+  // ---- CTA pairs ----
+  {
+    static int want_pair = -1;
+    if (want_pair < 0) {
+      const char* e = getenv("COCLR_TMA_PAIR");
+      want_pair = (e && e[0] == '1') ? 1 : 0;
+    }
+    L.pair = (want_pair && mt >= 2 && L.BN % 16 == 0) ? 1 : 0;
+    L.pair_items = (int)(((mt + 1) / 2) * L.n_tiles_n);
+  }
   // ---- shared memory ----
   L.plane_stride = (L.slab_bytes + 1023) & ~1023;
   L.a_slot_bytes = planes * L.plane_stride;
   L.b_tile_bytes = planes * L.BN * 128;
+  if (L.pair) L.b_tile_bytes = (L.stacked ? 3 : planes) * (L.BN / 2) * 128;
   const int budget = 227 * 1024 - 1024 /*alignment slack*/ - 1024 /*unscale table*/ - 256 /*barriers*/;
   const int stage1 = 4 * (int)kStageBytes, stage2 = 8 * (int)kStageBytes;
   int steps_per_tile = 0;
   for (int ty = 0; ty < L.n_types; ++ty) steps_per_tile += L.type[ty].nshift;
   steps_per_tile *= L.nc;
-  const long tiles_per_cta = ((long)L.total_tiles + 147) / 148;
+  const long tiles_per_cta = L.pair ? ((long)L.pair_items + 73) / 74 : ((long)L.total_tiles + 147) / 148;
   L.b_resident = 0;
   const long resident_bytes = (long)L.nkc * L.b_tile_bytes;
   if (L.n_tiles_n == 1 && tiles_per_cta >= 2 && resident_bytes + 2l * L.a_slot_bytes + stage1 <= budget) {
@@ -758,7 +864,9 @@ static bool conv_tma_plan_variant(const coclr_conv_t& P, int variant, TmaPlan& L
 bool conv_tma_plan(const coclr_conv_t& P, TmaPlan& L, MapSpec& A, MapSpec& O) {
   bool have = false;
   long best = -1;
+  const char* fv = getenv("COCLR_TMA_VARIANT");      // tuning experiments: force one tile-shape variant
   for (int v = 0; v < 3; ++v) {
+    if (fv && atoi(fv) != v) continue;
     TmaPlan l;
     MapSpec a, o;
     if (!conv_tma_plan_variant(P, v, l, a, o)) continue;
@@ -810,7 +918,7 @@ int coclr::conv_tma_try(const coclr_conv_t& P, int num_sms, cudaStream_t stream)
   TmaArgs args;
   MapSpec A, O;
   if (!conv_tma_plan(P, args.plan, A, O)) return 1;
-  CUtensorMap m_hi, m_lo, m_out;
+  CUtensorMap m_hi, m_lo, m_out, m_w;
   if (!encode_map(&m_hi, A, 0)) return 1;
   if (P.npass > 1) {
     if (!encode_map(&m_lo, A, 1)) return 1;
@@ -818,6 +926,24 @@ int coclr::conv_tma_try(const coclr_conv_t& P, int num_sms, cudaStream_t stream)
     m_lo = m_hi;
   }
   if (!encode_map(&m_out, O, 0)) return 1;
+  const TmaPlan& L = args.plan;
+  m_w = m_hi;
+  if (L.pair) {
+    // the packed weight image as rows of 128 bytes (64 16-bit elements): BN/2-row boxes, copied as they are
+    MapSpec Wm;
+    Wm.elem_bytes = 2;
+    Wm.base[0] = const_cast<void*>(P.wpk);
+    Wm.base[1] = nullptr;
+    Wm.dims[0] = 64;
+    Wm.dims[1] = (uint64_t)L.n_tiles_n * L.nkc * 2 * L.BN;
+    Wm.dims[2] = Wm.dims[3] = Wm.dims[4] = 1;
+    Wm.strides[0] = 128;
+    Wm.strides[1] = Wm.strides[2] = Wm.strides[3] = 128;
+    Wm.box[0] = 64;
+    Wm.box[1] = (uint32_t)(L.BN / 2);
+    Wm.box[2] = Wm.box[3] = Wm.box[4] = 1;
+    if (((uintptr_t)P.wpk & 15) || !encode_map(&m_w, Wm, 0, 2, false)) return 1;
+  }
   args.wpk = P.wpk;
   args.wunscale = P.wunscale;
   args.out_scale = P.out_scale;
@@ -826,17 +952,35 @@ int coclr::conv_tma_try(const coclr_conv_t& P, int num_sms, cudaStream_t stream)
   args.accumulate = P.accumulate;
   args.a_bf16 = P.a_bf16;
   args.b_bf16 = P.b_bf16;
-  const TmaPlan& L = args.plan;
-  const int grid = L.total_tiles < num_sms ? L.total_tiles : num_sms;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(kTmaThreads);
+  cfg.dynamicSmemBytes = L.total;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
   cudaError_t e;
-  if (P.npass > 1) {
-    e = cudaFuncSetAttribute(conv_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-    if (e != cudaSuccess) return COCLR_E_LAUNCH;
-    conv_tma_kernel<3><<<grid, kTmaThreads, L.total, stream>>>(m_hi, m_lo, m_out, args);
+#define COCLR_TMA_LAUNCH(NP, PAIR)                                                                                    \
+  do {                                                                                                                \
+    e = cudaFuncSetAttribute(conv_tma_kernel<NP, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);   \
+    if (e != cudaSuccess) return COCLR_E_LAUNCH;                                                                      \
+    e = cudaLaunchKernelEx(&cfg, conv_tma_kernel<NP, PAIR>, m_hi, m_lo, m_out, m_w, args);                            \
+  } while (0)
+  if (L.pair) {
+    const int pairs = num_sms / 2;
+    const int nclusters = L.pair_items < pairs ? L.pair_items : pairs;
+    cfg.gridDim = dim3(2 * nclusters);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (P.npass > 1) COCLR_TMA_LAUNCH(3, true); else COCLR_TMA_LAUNCH(1, true);
   } else {
-    e = cudaFuncSetAttribute(conv_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-    if (e != cudaSuccess) return COCLR_E_LAUNCH;
-    conv_tma_kernel<1><<<grid, kTmaThreads, L.total, stream>>>(m_hi, m_lo, m_out, args);
+    cfg.gridDim = dim3(L.total_tiles < num_sms ? L.total_tiles : num_sms);
+    if (P.npass > 1) COCLR_TMA_LAUNCH(3, false); else COCLR_TMA_LAUNCH(1, false);
   }
+#undef COCLR_TMA_LAUNCH
+  if (e != cudaSuccess) return COCLR_E_LAUNCH;
   return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
 }

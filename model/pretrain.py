@@ -180,7 +180,10 @@ class InfoNCE(nn.Module):
         # so that the many small layers of the two encoders fill the SMs together
         main = torch.cuda.current_stream()
         if self._side_stream is None:
-            self._side_stream = torch.cuda.Stream()
+            # high priority: the key branch carries the cross-rank exchange (clip publish, barrier, permutation broadcast,
+            # NVLink reads); when it gets the SMs first, that latency is covered by the query forward on the main stream
+            # instead of sticking out behind it
+            self._side_stream = torch.cuda.Stream(priority=-1)
         side = self._side_stream if InfoNCE.overlap_key_branch else main
         side.wait_stream(main)
         with torch.cuda.stream(side), torch.no_grad():
@@ -251,7 +254,7 @@ class CoCLR(InfoNCE):
         in_train_mode = torch.is_grad_enabled() and any(p.requires_grad for p in self.encoder_q.parameters())
         main = torch.cuda.current_stream()
         if self._side_stream is None:
-            self._side_stream = torch.cuda.Stream()
+            self._side_stream = torch.cuda.Stream(priority=-1)     # key branch first: it carries the cross-rank exchange
         if getattr(self, "_side_stream2", None) is None:
             self._side_stream2 = torch.cuda.Stream()
         side = self._side_stream if CoCLR.overlap_branches else main
