@@ -44,6 +44,8 @@ def parse():
                     help="infonce = configs 1-3,5; coclr = config 4 (2-stream co-training step: q fwd+bwd, k fwd, frozen "
                          "sampler fwd, top-k mined positives)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the first step")
+    ap.add_argument("--no-mixed", action="store_true",
+                    help="skip the extra `--precision mixed` measurement reported under config.mixed_precision")
     ap.add_argument("--no-stock-gpu", action="store_true", help="skip the stock-PyTorch-on-this-GPU baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -533,6 +535,32 @@ def main():
         for msl, name, desc, tf in rows[:60]:
             print("%8.3f ms %-18s %-40s %7.1f TF/s" % (msl, name[6:], desc, tf), file=sys.stderr)
 
+    # ---- the same step with the single-pass fp16 backward (`--precision mixed`): identical forward, hence identical
+    #      logits / loss / queue parity; NOT the headline (see DESIGN.md section 3 "precision modes") ----
+    mixed = None
+    if args.precision == "parity" and not args.no_mixed and not coclr:
+        del model, opt
+        torch.cuda.empty_cache()
+        torch.manual_seed(0)
+        model = InfoNCE(args.net, CFG["dim"], K, CFG["m"], CFG["T"], precision="mixed").to(dev).train()
+        opt = moco.FlatAdam(model.encoder_q, lr=1e-3, weight_decay=1e-5)
+        for i in range(max(3, args.warmup)):
+            train_step(dev_blocks[i % 2])
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for i in range(args.steps):
+            train_step(dev_blocks[i % 2])
+        m1.record()
+        barrier()
+        mt = torch.tensor([m0.elapsed_time(m1) / args.steps], device=dev)
+        if world > 1:
+            dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+        mixed = {"precision": "mixed (parity forward, single-pass fp16 backward on scaled gradient planes)",
+                 "ms_per_step": float(mt), "value": 2.0 * B * world / (float(mt) * 1e-3), "unit": "clips/s",
+                 "note": "same logits / loss / queue as the headline; gradients within the oracle-relative budget at "
+                         "random init (tests/test_infonce_gpu.py::test_other_precisions_report), a real precision cut "
+                         "in well-conditioned regimes -- opt-in, not the headline"}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -565,7 +593,8 @@ def main():
                            "global_batch": B * world, "parallelism": "dp%d" % world, "precision": args.precision,
                            "l2": "two alternating 403 MB input blocks per rank (> 126 MB L2)",
                            "pairs_per_s": value / 2, "final_loss": final_loss, "host_enqueue_ms_per_step": host_ms,
-                           "algorithmic_tflops": value / 2 * GFLOP_PER_PAIR[args.net] * (1.25 if coclr else 1.0) * (T / 32.0) / 1e3},
+                           "algorithmic_tflops": value / 2 * GFLOP_PER_PAIR[args.net] * (1.25 if coclr else 1.0) * (T / 32.0) / 1e3,
+                           "mixed_precision": mixed},
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "parity": parity, "replicas_identical": same_replicas}
         if stock is not None:

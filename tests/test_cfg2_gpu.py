@@ -104,8 +104,8 @@ def test_cfg2_gradients(step2, diag):
     diag["cfg2/grad_err_new_vs_ref"] = out
     diag["cfg2/grad_exceptions"] = bad
     assert len(out) == 235
-    assert med_new < 2 * med_ref + 1e-3, (med_new, med_ref)
-    assert len(bad) <= 4, bad[:8]        # a handful of tiny BatchNorm-bias gradients sit at the noise floor
+    assert med_new < 1.5 * med_ref + 1e-3, (med_new, med_ref)      # measured 2.6e-2 vs 2.0e-2
+    assert len(bad) <= 2, bad[:8]
 
 
 @pytest.mark.parametrize("Kq,Bq", [(16384, 32), (16384, 256), (2048, 32)])

@@ -165,16 +165,17 @@ def test_gradients_oracle_relative(step, diag):
         e_new = _rel_l2(named[k].grad, g64)
         e_ref = _rel_l2(sd32[k].grad, g64)
         out[k] = [e_new, e_ref]
-        if not e_new < 0.2:     # no tensor may be grossly wrong ...
+        if not e_new < max(5 * e_ref, 3e-2):     # no tensor may be grossly wrong ...
             bad.append((k, e_new, e_ref))
     diag["infonce/grad_err_new_vs_ref"] = out
-    # ... and, over the 235 tensors, our deviation from the float64 truth stays within 3x the deviation the
+    # ... and, over the 235 tensors, our deviation from the float64 truth stays within 1.5x the deviation the
     # reference's own fp32 arithmetic shows (the gradient of this saturated loss is ill-conditioned: fp32 itself
-    # is ~2e-2 off, SURVEY.md section 7 "hard parts")
+    # is ~2e-2 off, SURVEY.md section 7 "hard parts").  Measured since the gradient planes are fp16 hi/lo with a
+    # per-tensor scale: 2.20e-2 against 2.17e-2 (with bf16 hi/lo planes it was 4.6e-2, which needed a 3x budget)
     med_new = float(np.median([v[0] for v in out.values()]))
     med_ref = float(np.median([v[1] for v in out.values()]))
     diag["infonce/grad_median_new_ref"] = [med_new, med_ref]
-    assert med_new < 3 * med_ref + 1e-3, (med_new, med_ref)
+    assert med_new < 1.5 * med_ref + 1e-3, (med_new, med_ref)
     gold = np.load(GOLD)
     diag["infonce/grad_vs_golden"] = {k[5:]: _rel_l2(named[k[5:]].grad, gold[k]) for k in gold.files if k.startswith("grad/")}
     assert not bad, bad[:5]
@@ -182,8 +183,11 @@ def test_gradients_oracle_relative(step, diag):
 
 @pytest.mark.parametrize("precision", ["mixed", "fast"])
 def test_other_precisions_report(step, diag, precision):
-    """Non-parity modes: record (not assert tightly) logits / gradient error of 'mixed' (fp32-grade forward,
-    single-pass bf16 backward) and 'fast' (single-pass bf16 everywhere) against the float64 oracle."""
+    """Non-parity modes against the float64 oracle.  'mixed' = the parity forward (same logits / loss / queue) with a
+    single-pass fp16 backward (scaled gradient planes, hi plane only): at this -- ill-conditioned, random-init -- state
+    its gradients are as close to the float64 truth as the 3-pass backward's and as fp32 torch's own, which is
+    asserted; in well-conditioned regimes a single 11-bit pass is a real precision cut, so it stays opt-in.
+    'fast' = single-pass bf16 everywhere (recorded only; far outside the parity bar)."""
     import make_golden as MG
     from coclr_b200 import moco
     model, sd = _build(precision=precision)
@@ -199,6 +203,11 @@ def test_other_precisions_report(step, diag, precision):
     diag["precision/%s" % precision] = {"logits_vs_fp64": _rel(logits, lg64), "grad_median": float(np.median(errs)),
                                         "grad_max": float(np.max(errs))}
     assert _rel(logits, lg64) < (1e-3 if precision == "mixed" else 0.5)
+    if precision == "mixed":
+        ref = step["ref32"][0]
+        ref_errs = [_rel_l2(ref[k].grad, sd64[k].grad) for k in sorted(sd64)
+                    if k.startswith("encoder_q.") and (k.endswith(".weight") or k.endswith(".bias"))]
+        assert float(np.median(errs)) < 2 * float(np.median(ref_errs)) + 1e-3
 
 
 def test_no_grad_eval_has_no_side_effects(step):
