@@ -24,6 +24,9 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 CFG = dict(network="s3d", dim=128, K=2048, m=0.999, T=0.07, B=32, seq_len=32, img=128)
+# bounded CPU sample of the workload (reference arm and cpu_baseline leg): 4 clip pairs of 16 frames = 4 of the benchmark's
+# 32-frame clips per step, ~1 s per step on 16 host cores -> ~10 s for the default 8 timed steps
+CPU_SAMPLE_BATCH, CPU_SAMPLE_T = 4, 16
 GFLOP_PER_PAIR = {"s3d": 91.46, "r50": 231.67}  # q fwd+dgrad+wgrad, k fwd (conv MACs x2), one clip pair
 NET_NAME = {"s3d": "S3D", "r50": "R2D3D-50"}
 
@@ -50,6 +53,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel time table of one step to stderr")
+    ap.add_argument("--timeline", action="store_true",
+                    help="per-phase CUDA-event timeline of one step (ms since step start, max over ranks) in the JSON line")
     return ap.parse_args()
 
 
@@ -137,8 +142,8 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch, sample_T = 1, 8
-    steps = max(1, min(args.steps, 3))
+    batch, sample_T = CPU_SAMPLE_BATCH, CPU_SAMPLE_T
+    steps = max(1, min(args.steps, 10))
     val, med = cpu_oracle_clips_per_s(batch, sample_T, CFG["img"], args.moco_k, steps, 1, args.net)
     line = {"impl": "reference", "metric": "clips/sec %s InfoNCE (32x128^2, K=%d)" % (NET_NAME[args.net], args.moco_k), "value": val, "unit": "clips/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": med * 1e3, "higher_is_better": True,
@@ -180,6 +185,9 @@ def parity_first_step(model, run_step, block, world, rank, dev):
     else:
         blocks_all, logits_all = block[None], logits.detach()[None]
     out = None
+    store = dist.distributed_c10d._get_default_store() if world > 1 else None
+    if rank != 0 and store is not None:
+        store.wait(["coclr_parity_done"])     # sleep in the store client instead of spinning next to rank 0's oracle run
     if rank == 0:
         t0 = time.perf_counter()
         prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
@@ -209,6 +217,8 @@ def parity_first_step(model, run_step, block, world, rank, dev):
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
         torch.cuda.synchronize()
         out["seconds"] = round(time.perf_counter() - t0, 2)
+        if store is not None:
+            store.set("coclr_parity_done", "1")
     del blocks_all, logits_all, sd0
     torch.cuda.empty_cache()
     return out
@@ -474,6 +484,23 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- per-phase timeline of one step (events on the streams the phases run on) ----
+    timeline = None
+    if args.timeline:
+        moco.TIMELINE = []
+        t_start = torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_start.record()
+        train_step(dev_blocks[0])
+        moco.mark("step:end")
+        torch.cuda.synchronize()
+        tl = [(name, t_start.elapsed_time(ev)) for name, ev in moco.TIMELINE]
+        moco.TIMELINE = None
+        vals = torch.tensor([v for _, v in tl], device=dev)
+        if world > 1:
+            dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        timeline = {name: round(float(v), 3) for (name, _), v in zip(tl, vals)}
+
     # ---- roofline of the dominant kernel, measured live with CUDA events around every launch of one step ----
     table, prof = kernel_breakdown(lambda: train_step(dev_blocks[0]))
     peaks = {}
@@ -565,10 +592,11 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             try:
-                v, med = cpu_oracle_clips_per_s(1, 8, HW, K, 2, 1, args.net)
+                v, med = cpu_oracle_clips_per_s(CPU_SAMPLE_BATCH, CPU_SAMPLE_T, HW, K, 8, 1, args.net)
                 cpu = {"value": v, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
-                       "sample": "oracle port (torch CPU fp32) full train step on 1 pair of 8-frame 128^2 clips "
-                                 "(= 0.5 clip of 32 frames), 2 timed steps after 1 warm-up, %.1f s/step" % med}
+                       "sample": "oracle port (torch CPU fp32) full train step on %d pairs of %d-frame 128^2 clips "
+                                 "(= %d clips of 32 frames), median of 8 timed steps after 1 warm-up, %.2f s/step"
+                                 % (CPU_SAMPLE_BATCH, CPU_SAMPLE_T, 2 * CPU_SAMPLE_BATCH * CPU_SAMPLE_T // 32, med)}
             except Exception as ex:  # pragma: no cover
                 cpu = {"value": None, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
                        "sample": "failed: %r" % (ex,)}
@@ -594,7 +622,7 @@ def main():
                            "l2": "two alternating 403 MB input blocks per rank (> 126 MB L2)",
                            "pairs_per_s": value / 2, "final_loss": final_loss, "host_enqueue_ms_per_step": host_ms,
                            "algorithmic_tflops": value / 2 * GFLOP_PER_PAIR[args.net] * (1.25 if coclr else 1.0) * (T / 32.0) / 1e3,
-                           "mixed_precision": mixed},
+                           "mixed_precision": mixed, "phase_timeline_ms": timeline},
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "parity": parity, "replicas_identical": same_replicas}
         if stock is not None:

@@ -20,7 +20,20 @@ from .engine import Graph, ParamStore, EncoderEngine
 from .s3d_spec import S3D_FEATURE_SIZE
 
 
-OVERLAP_ALLREDUCE = os.environ.get("COCLR_OVERLAP_ALLREDUCE", "1") != "0"
+# Split all-reduce started in the middle of backward (see _EncodeFn.backward).  Off by default: on 8 x B200 over NVSwitch
+# the 36 MB all-reduce is 0.18 ms when it runs alone after backward, while running it next to the backward kernels
+# lengthened backward by 0.3 ms (profiles/r02_scale8_timeline.json); COCLR_OVERLAP_ALLREDUCE=1 enables it.
+OVERLAP_ALLREDUCE = os.environ.get("COCLR_OVERLAP_ALLREDUCE", "0") == "1"
+
+# Per-phase timeline of a step (bench.py --timeline): CUDA events on whatever stream the phase runs on; off by default.
+TIMELINE = None
+
+
+def mark(name):
+    if TIMELINE is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        TIMELINE.append((name, ev))
 
 
 def _world():
@@ -95,8 +108,10 @@ class _EncodeFn(torch.autograd.Function):
             def hook(ranges):      # async all-reduce on the process group's stream; FlatAdam.step() waits for them
                 for lo, hi in ranges:
                     st.pending_reduce.append(dist.all_reduce(st.grad[lo:hi], async_op=True))
+        mark("bwd:start")
         if not enc._engine.backward(ctx.plan, dq.contiguous(), mid_hook=hook) and hook is not None:
             st.pending_reduce = None      # un-split launch list: FlatAdam.step() reduces the whole buffer
+        mark("bwd:end")
         return None, None, None, None
 
 
@@ -290,12 +305,14 @@ class FlatAdam:
         st = self._state()
         world, _ = _world()
         pending = getattr(st, "pending_reduce", None)
+        mark("opt:allreduce_wait")
         if pending:
             for work in pending:          # the ranges were all-reduced while the backward pass was still running
                 work.wait()
         elif world > 1:
             dist.all_reduce(st.grad)
         st.pending_reduce = None
+        mark("opt:allreduce_done")
         g = self.param_groups[0]
         self.step_count += 1
         b1, b2 = g["betas"]
@@ -304,6 +321,7 @@ class FlatAdam:
         p = L.Adam(L.dptr(st.flat), L.dptr(st.grad), L.dptr(self.exp_avg), L.dptr(self.exp_avg_sq), st.numel,
                    1.0 / world, b1, b2, g["eps"], g["weight_decay"], g["lr"] / bc1, math.sqrt(bc2))
         L.check(L.load().coclr_adam_step(C.byref(p), L.num_sms(st.flat.device), L.stream_ptr()), "coclr_adam_step")
+        mark("opt:adam_done")
 
     def state_dict(self):
         return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,

@@ -125,19 +125,32 @@ class InfoNCE(nn.Module):
         world, rank = moco._world()
         B = x2.shape[0]
         peer = self._peer_exchange(x2) if world > 1 else None
+        moco.mark("key:start")
         if peer is None:
             x_gather = concat_all_gather(x2) if world > 1 else x2                     # :105-106
         else:
             x_gather, peer_ptrs = peer.publish(x2)      # own clips; the other ranks' are read in place over NVLink
-        idx_shuffle = torch.randperm(B * world).to(x2.device, non_blocking=True)     # CPU RNG draw, as :112
+        moco.mark("key:clips_published")
+        # CPU RNG draw as in the reference (:112); staged through pinned memory so that the host does not block on the copy
+        if getattr(self, "_perm_pinned", None) is None or self._perm_pinned[0].numel() != B * world:
+            self._perm_pinned = [torch.empty(B * world, dtype=torch.long).pin_memory() for _ in range(2)]
+            self._perm_flip = 0
+        pinned = self._perm_pinned[self._perm_flip]
+        self._perm_flip ^= 1
+        torch.randperm(B * world, out=pinned)
+        idx_shuffle = torch.empty(B * world, dtype=torch.long, device=x2.device)
+        idx_shuffle.copy_(pinned, non_blocking=True)
         if world > 1:
             dist.broadcast(idx_shuffle, src=0)                                       # :115
+        moco.mark("key:perm_broadcast")
         idx_unshuffle = torch.argsort(idx_shuffle)
         idx_this = idx_shuffle.view(world, -1)[rank].contiguous()
         k_sh = encoder.encode(x_gather, batch_index=idx_this, batch=B,            # x_gather[idx_this], :124
                               peers=(peer_ptrs, B) if peer is not None else None)
+        moco.mark("key:encoded")
         k_all = concat_all_gather(k_sh) if world > 1 else k_sh
         k_global = k_all[idx_unshuffle].contiguous()                                  # :143 for every rank
+        moco.mark("key:gathered")
         return k_global[rank * B:(rank + 1) * B], k_global
 
     peer_shuffle = os.environ.get("COCLR_PEER_SHUFFLE", "1") != "0"
@@ -186,12 +199,23 @@ class InfoNCE(nn.Module):
             self._side_stream = torch.cuda.Stream(priority=-1)
         side = self._side_stream if InfoNCE.overlap_key_branch else main
         side.wait_stream(main)
+        overlap = side is not main
+        if overlap:
+            # the query forward is enqueued FIRST: the key branch has host-side work (permutation draw, collectives) that
+            # would otherwise keep the main stream idle for the first ~1 ms of the step
+            moco.mark("query:start")
+            q = self.encoder_q.encode(x1)                                             # :153-155
+            moco.mark("query:encoded")
         with torch.cuda.stream(side), torch.no_grad():
             if in_train_mode:
                 self._momentum_update_key_encoder()                                   # :161
             k, k_global = self._shuffled_keys(x2)
-        q = self.encoder_q.encode(x1)                                                 # :153-155
+        if not overlap:
+            moco.mark("query:start")
+            q = self.encoder_q.encode(x1)                                             # :153-155
+            moco.mark("query:encoded")
         main.wait_stream(side)
+        moco.mark("joined")
         return q, k, k_global, in_train_mode
 
     def forward(self, block):
@@ -261,13 +285,17 @@ class CoCLR(InfoNCE):
         side2 = self._side_stream2 if CoCLR.overlap_branches else main
         side.wait_stream(main)
         side2.wait_stream(main)
+        overlap = side is not main
+        if overlap:
+            q = self.encoder_q.encode(x1)           # enqueued first (the key branch has host-side work, see InfoNCE._qk)
         with torch.cuda.stream(side), torch.no_grad():
             if in_train_mode:
                 self._momentum_update_key_encoder()
             k, k_global = self._shuffled_keys(x2)
         with torch.cuda.stream(side2), torch.no_grad():
             kf = self.sampler.encode(f2)                                              # :372-374 (no shuffle)
-        q = self.encoder_q.encode(x1)
+        if not overlap:
+            q = self.encoder_q.encode(x1)
         main.wait_stream(side)
         main.wait_stream(side2)
         for t in (k, k_global, kf):

@@ -46,7 +46,9 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__grid_size", "launch__block_size", "sm__cycles_elapsed.max", "smsp__inst_executed.sum",
         "launch__shared_mem_per_block_dynamic", "l1tex__m_xbar2l1tex_read_bytes.sum",
         "l1tex__m_xbar2l1tex_read_bytes.sum.per_second", "sm__inst_executed.avg.per_cycle_elapsed",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct"]
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum.per_second",
+        "dram__bytes_write.sum.per_second", "sm__inst_executed_pipe_tensor.sum"]
 
 
 def full(reps):
@@ -55,12 +57,13 @@ def full(reps):
         txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(txt.splitlines()))
         hdr, units = rows[0], rows[1]
-        for vals in rows[2:]:
+        for n_launch, vals in enumerate(rows[2:]):
             d = {}
             for h, u, v in zip(hdr, units, vals):
                 if h in WANT or h == "Kernel Name":
                     d[h] = v if h == "Kernel Name" else {"value": float(v.replace(",", "")) if v else None, "unit": u}
-            out[rep.split("/")[-1]] = d
+            key = rep.split("/")[-1]
+            out[key if n_launch == 0 else "%s#%d" % (key, n_launch)] = d
     json.dump(out, sys.stdout, indent=1)
 
 
