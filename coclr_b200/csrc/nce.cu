@@ -92,13 +92,111 @@ __global__ void __launch_bounds__(kNceThreads) nce_bwd_kernel(const float* __res
   }
 }
 
+// Long queues (config 3: K = 16384): one CTA per row leaves most of the 148 SMs idle and every CTA streams the whole
+// [D, K] queue through L2.  The split form cuts a row into K slices of kNceSlice columns on blockIdx.y:
+//   pass 1 (nce_fwd_slice_kernel): logits of the slice + the slice's (max, sum exp(l - max)) into ws[b][slice][2];
+//   pass 2 (nce_fwd_finish_kernel): every CTA folds the row's partials into the log-sum-exp, then loss / dlogits of its slice.
+static constexpr int kNceSlice = 1024;
+
+__global__ void __launch_bounds__(256) nce_fwd_slice_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                            const float* __restrict__ queue, float T, int D, int K,
+                                                            float* __restrict__ logits, float* __restrict__ ws) {
+  extern __shared__ float sm[];
+  float* sq = sm;        // [D]
+  float* red = sm + D;   // [32]
+  const int b = blockIdx.x, sl = blockIdx.y, nsl = gridDim.y;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) sq[c] = q[(long)b * D + c];
+  __syncthreads();
+  float* lrow = logits + (long)b * (K + 1);
+  float mx = -INFINITY;
+  if (sl == 0) {   // the positive logit belongs to slice 0
+    float pp = 0.f;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) pp += sq[c] * k[(long)b * D + c];
+    const float lpos = block_reduce(pp, red, false) / T;
+    if (threadIdx.x == 0) lrow[0] = lpos;
+    mx = lpos;
+  }
+  const int j0 = sl * kNceSlice, j1 = min(K, j0 + kNceSlice);
+  float mine[kNceSlice / 256];
+#pragma unroll
+  for (int u = 0; u < kNceSlice / 256; ++u) {
+    const int j = j0 + u * 256 + threadIdx.x;
+    float a = -INFINITY;
+    if (j < j1) {
+      a = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < D; ++c) a = fmaf(sq[c], __ldg(queue + (long)c * K + j), a);
+      a = a / T;
+      lrow[1 + j] = a;
+    }
+    mine[u] = a;
+    mx = fmaxf(mx, a);
+  }
+  mx = block_reduce(mx, red, true);
+  float se = 0.f;
+#pragma unroll
+  for (int u = 0; u < kNceSlice / 256; ++u) se += __expf(mine[u] - mx);      // exp(-inf) = 0 for the padded tail
+  if (sl == 0 && threadIdx.x == 0) se += __expf(lrow[0] - mx);
+  __syncthreads();
+  se = block_reduce(se, red, false);
+  if (threadIdx.x == 0) {
+    ws[((long)b * nsl + sl) * 2 + 0] = mx;
+    ws[((long)b * nsl + sl) * 2 + 1] = se;
+  }
+}
+
+__global__ void __launch_bounds__(256) nce_fwd_finish_kernel(const float* __restrict__ logits, const float* __restrict__ ws,
+                                                             int B, int K, float* __restrict__ loss_rows,
+                                                             float* __restrict__ dlogits) {
+  const int b = blockIdx.x, sl = blockIdx.y, nsl = gridDim.y;
+  float mx = -INFINITY;
+  for (int s = 0; s < nsl; ++s) mx = fmaxf(mx, ws[((long)b * nsl + s) * 2]);
+  float se = 0.f;
+  for (int s = 0; s < nsl; ++s) se += ws[((long)b * nsl + s) * 2 + 1] * __expf(ws[((long)b * nsl + s) * 2] - mx);
+  const float lse = mx + logf(se);
+  const float* lrow = logits + (long)b * (K + 1);
+  if (sl == 0 && threadIdx.x == 0 && loss_rows) loss_rows[b] = lse - lrow[0];
+  if (dlogits) {
+    const float invB = 1.f / (float)B;
+    float* drow = dlogits + (long)b * (K + 1);
+    const int j0 = sl * kNceSlice, j1 = min(K, j0 + kNceSlice);
+    if (sl == 0 && threadIdx.x == 0) drow[0] = (__expf(lrow[0] - lse) - 1.f) * invB;
+    for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) drow[1 + j] = __expf(lrow[1 + j] - lse) * invB;
+  }
+}
+
+// dq over a K slice, accumulated with fp32 atomics (dq zeroed by the caller path below)
+__global__ void __launch_bounds__(256) nce_bwd_slice_kernel(const float* __restrict__ dlogits, const float* __restrict__ k,
+                                                            const float* __restrict__ queue, float T, int D, int K,
+                                                            float* __restrict__ dq) {
+  __shared__ float sd[kNceSlice];
+  const int b = blockIdx.x, sl = blockIdx.y;
+  const int j0 = sl * kNceSlice, n = min(K - j0, kNceSlice);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) sd[j] = dlogits[(long)b * (K + 1) + 1 + j0 + j];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float d0 = dlogits[(long)b * (K + 1)];
+  for (int c = w; c < D; c += nw) {
+    float a = 0.f;
+    for (int j = lane; j < n; j += 32) a = fmaf(sd[j], __ldg(queue + (long)c * K + j0 + j), a);
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) atomicAdd(dq + (long)b * D + c, (a + (sl == 0 ? d0 * k[(long)b * D + c] : 0.f)) / T);
+  }
+}
+
 }  // namespace coclr
 
 using namespace coclr;
 
 extern "C" int coclr_nce_logits_ce(const float* q, const float* k, const float* queue, float T, int B, int D, int K,
-                                   float* logits, float* loss_rows, float* dlogits, coclr_stream_t stream) {
+                                   float* logits, float* loss_rows, float* dlogits, float* ws, coclr_stream_t stream) {
   if (!q || !k || !queue || !logits || B <= 0 || D <= 0 || K <= 0) return COCLR_E_ARG;
+  if (ws != nullptr && K > 2 * kNceSlice) {
+    const dim3 grid(B, (K + kNceSlice - 1) / kNceSlice);
+    nce_fwd_slice_kernel<<<grid, 256, (D + 32) * sizeof(float), (cudaStream_t)stream>>>(q, k, queue, T, D, K, logits, ws);
+    nce_fwd_finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, ws, B, K, loss_rows, dlogits);
+    return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
+  }
   nce_fwd_kernel<<<B, kNceThreads, (D + 32) * sizeof(float), (cudaStream_t)stream>>>(q, k, queue, T, B, D, K, logits,
                                                                                     loss_rows, dlogits);
   return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
@@ -107,6 +205,12 @@ extern "C" int coclr_nce_logits_ce(const float* q, const float* k, const float* 
 extern "C" int coclr_nce_logits_bwd(const float* dlogits, const float* k, const float* queue, float T, int B, int D,
                                     int K, float* dq, coclr_stream_t stream) {
   if (!dlogits || !k || !queue || !dq) return COCLR_E_ARG;
+  if (K > 2 * kNceSlice) {
+    if (cudaMemsetAsync(dq, 0, sizeof(float) * (size_t)B * D, (cudaStream_t)stream) != cudaSuccess) return COCLR_E_LAUNCH;
+    const dim3 grid(B, (K + kNceSlice - 1) / kNceSlice);
+    nce_bwd_slice_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dlogits, k, queue, T, D, K, dq);
+    return cudaGetLastError() == cudaSuccess ? COCLR_OK : COCLR_E_LAUNCH;
+  }
   const size_t smem = (size_t)(K + 1) * sizeof(float);
   if (smem > 200 * 1024) return COCLR_E_ARG;
   if (smem > 48 * 1024) {

@@ -225,8 +225,9 @@ class _NCELogitsFn(torch.autograd.Function):
         logits = torch.empty(B, K + 1, dtype=torch.float32, device=q.device)
         loss_rows = torch.empty(B, dtype=torch.float32, device=q.device)
         dlogits = torch.empty(B, K + 1, dtype=torch.float32, device=q.device)
+        ws = torch.empty(2 * B * ((K + 1023) // 1024), dtype=torch.float32, device=q.device) if K > 2048 else None
         L.check(L.load().coclr_nce_logits_ce(L.dptr(q), L.dptr(k), L.dptr(queue), float(T), B, D, K, L.dptr(logits),
-                                             L.dptr(loss_rows), L.dptr(dlogits), L.stream_ptr()),
+                                             L.dptr(loss_rows), L.dptr(dlogits), L.dptr(ws), L.stream_ptr()),
                 "coclr_nce_logits_ce")
         # the queue is overwritten by the enqueue right after (pretrain.py:188); backward needs the old one
         ctx.save_for_backward(k, queue.clone())

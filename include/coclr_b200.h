@@ -294,9 +294,11 @@ int coclr_adam_step(const coclr_adam_t* p, int num_sms, coclr_stream_t stream);
 
 /* ---- InfoNCE logits + temperature + cross-entropy (model/pretrain.py:175-182; main_nce.py:201,314) ----
  * logits[b, 0] = q_b.k_b / T, logits[b, 1+j] = q_b.queue[:, j] / T; loss_rows[b] = logsumexp - logits[b,0];
- * dlogits = d(mean_b loss_rows)/d(logits).  loss_rows / dlogits may be NULL. */
+ * dlogits = d(mean_b loss_rows)/d(logits).  loss_rows / dlogits may be NULL.
+ * ws: optional scratch of 2 * B * ceil(K / 1024) floats; with it, queues longer than 2048 are cut into 1024-column
+ * slices on separate CTAs (config 3: K = 16384 would otherwise run on B of the 148 SMs). */
 int coclr_nce_logits_ce(const float* q, const float* k, const float* queue, float T, int B, int D, int K,
-                        float* logits, float* loss_rows, float* dlogits, coclr_stream_t stream);
+                        float* logits, float* loss_rows, float* dlogits, float* ws, coclr_stream_t stream);
 /* dq = d(logits)^T contraction with [k | queue] / T (no gradient to k or the queue, pretrain.py:160,176) */
 int coclr_nce_logits_bwd(const float* dlogits, const float* k, const float* queue, float T, int B, int D, int K,
                          float* dq, coclr_stream_t stream);

@@ -133,7 +133,9 @@ class InfoNCE(nn.Module):
         moco.mark("key:clips_published")
         # CPU RNG draw as in the reference (:112); staged through pinned memory so that the host does not block on the copy
         if getattr(self, "_perm_pinned", None) is None or self._perm_pinned[0].numel() != B * world:
-            self._perm_pinned = [torch.empty(B * world, dtype=torch.long).pin_memory() for _ in range(2)]
+            self._perm_pinned = [torch.empty(B * world, dtype=torch.long) for _ in range(2)]
+            if x2.is_cuda:
+                self._perm_pinned = [t.pin_memory() for t in self._perm_pinned]
             self._perm_flip = 0
         pinned = self._perm_pinned[self._perm_flip]
         self._perm_flip ^= 1
@@ -267,12 +269,10 @@ class CoCLR(InfoNCE):
 
     overlap_branches = True   # query, key and sampler encoders on three streams (they only share read-only inputs)
 
-    def forward(self, block1, block2, k_vsource):
-        x1, f1 = self._views(block1)
-        x2, f2 = self._views(block2)
-        if self.reverse:                                                              # :353-355
-            x1, f1 = f1, x1
-            x2, f2 = f2, x2
+    def _qkf(self, x1, x2, f2):
+        """The three encoder passes of a step -- query (gradient), key (shuffle-BN, no gradient) and the frozen sampler on
+        the second view -- on three streams; they only share read-only inputs (reference pretrain.py:358-374 runs them
+        one after the other)."""
         if not x1.is_cuda:
             raise moco.L.CoclrError("coclr_b200 modules run on CUDA (sm_100a) only; there is no CPU path")
         in_train_mode = torch.is_grad_enabled() and any(p.requires_grad for p in self.encoder_q.parameters())
@@ -300,6 +300,15 @@ class CoCLR(InfoNCE):
         main.wait_stream(side2)
         for t in (k, k_global, kf):
             t.record_stream(main)
+        return q, k, k_global, kf, in_train_mode
+
+    def forward(self, block1, block2, k_vsource):
+        x1, f1 = self._views(block1)
+        x2, f2 = self._views(block2)
+        if self.reverse:                                                              # :353-355
+            x1, f1 = f1, x1
+            x2, f2 = f2, x2
+        q, k, k_global, kf, in_train_mode = self._qkf(x1, x2, f2)
         logits = moco.nce_logits(q, k, self.queue, self.T)
         if not self.queue_is_full:
             self.queue_is_full = bool(torch.all(self.queue_label != -1))              # :400-402

@@ -124,8 +124,9 @@ def test_nce_kernels_long_queue(Kq, Bq, diag):
     dlogits = torch.empty(Bq, Kq + 1, device="cuda")
     dq = torch.empty(Bq, D, device="cuda")
     lib = L.load()
+    ws = torch.empty(2 * Bq * ((Kq + 1023) // 1024), device="cuda")       # long queues: K slices on separate CTAs
     L.check(lib.coclr_nce_logits_ce(L.dptr(q), L.dptr(k), L.dptr(queue), Tt, Bq, D, Kq, L.dptr(logits), L.dptr(loss_rows),
-                                    L.dptr(dlogits), L.stream_ptr()), "coclr_nce_logits_ce")
+                                    L.dptr(dlogits), L.dptr(ws), L.stream_ptr()), "coclr_nce_logits_ce")
     L.check(lib.coclr_nce_logits_bwd(L.dptr(dlogits), L.dptr(k), L.dptr(queue), Tt, Bq, D, Kq, L.dptr(dq),
                                      L.stream_ptr()), "coclr_nce_logits_bwd")
     torch.cuda.synchronize()

@@ -92,6 +92,19 @@ def _stub_kernels(m, moco):
     moco.momentum_update = lambda q, k, mm: None
     moco.nce_logits = lambda q, k, queue, T: torch.cat([(q * k).sum(1, keepdim=True), q @ queue.clone()], 1) / T
 
+    def mask_topk(kf, queue_second, k_vsource, queue_vname, topk):     # the reference's statements (pretrain.py:392-413)
+        src = k_vsource.unsqueeze(1) == queue_vname.unsqueeze(0)
+        mask = src.clone()
+        if topk:
+            sim = kf.matmul(queue_second.clone())
+            sim[src] = -float("inf")
+            _, idx = torch.topk(sim, topk, dim=1)
+            onehot = torch.zeros_like(sim)
+            onehot.scatter_(1, idx, 1)
+            mask[onehot.bool()] = True
+        return torch.cat([torch.ones((mask.shape[0], 1), dtype=torch.bool), mask], dim=1)
+    moco.mask_topk = mask_topk
+
 
 def _worker_ext(rank, world, port, out):
     sys.path.insert(0, ROOT)
@@ -127,6 +140,14 @@ def _worker_ext(rank, world, port, out):
         c = P.CoCLR("s3d", 128, K, topk=3)
         _stub_kernels(c, moco)
         c.encoder_q.encode = lambda x, **kw: _fake_encode(x) * torch.ones(1, requires_grad=True)   # q must require grad (train mode)
+
+        def qkf_cpu(x1, x2, f2):      # CoCLR._qkf without its CUDA stream handling
+            with torch.no_grad():
+                c._momentum_update_key_encoder()
+                k, k_global = c._shuffled_keys(x2)
+                kf = c.sampler.encode(f2)
+            return c.encoder_q.encode(x1), k, k_global, kf, True
+        c._qkf = qkf_cpu
         c.queue_label[:] = 1                                     # queue full -> top-k branch
         c.queue_vname[:] = torch.arange(K) % 7
         b1 = torch.randn(B, 2, 3, 2, 8, 8, generator=g)
