@@ -558,6 +558,20 @@ def main():
             elif name in ("coclr_bn_bwd", "coclr_affine_split"):
                 o = a[0]._obj
                 rows.append((s0.elapsed_time(s1), name, "M=%d C=%d" % (o.M, o.C), 0.0))
+        # conv time by pixel count of the launch (which resolution level of the network it belongs to)
+        by_m = {}
+        for name, a, s0, s1 in prof:
+            if name == "coclr_conv_igemm":
+                o = a[0]._obj
+                m = o.B * o.Td * o.Hd * o.Wd
+                e = by_m.setdefault(m, [0, 0.0, 0.0])
+                e[0] += 1
+                e[1] += s0.elapsed_time(s1)
+                e[2] += conv_flops(o)
+        for m in sorted(by_m, reverse=True):
+            n, msl, fl = by_m[m]
+            print("conv_igemm launches with M=%-9d: %3d launches %7.3f ms %7.1f TF/s" % (m, n, msl, fl / (msl * 1e-3) / 1e12),
+                  file=sys.stderr)
         rows.sort(reverse=True)
         for msl, name, desc, tf in rows[:60]:
             print("%8.3f ms %-18s %-40s %7.1f TF/s" % (msl, name[6:], desc, tf), file=sys.stderr)

@@ -619,6 +619,123 @@ __global__ void __launch_bounds__(256) maxpool333_fwd_kernel(const coclr_pool_t 
   }
 }
 
+// 3x3x3 / stride 1 / pad 1 through shared memory (the form the launcher uses when W >= 8): a CTA owns (clip, 8 output
+// rows, all W columns, 16 channels) and walks along t.  Every input frame tile (10 x (W+2) pixels, -inf outside the
+// image) is staged ONCE with 16-byte cp.async copies -- the next frame's copies are in flight while the current one is
+// reduced -- so an input element leaves L2 1.25 times instead of 13.5 times (the register-only kernel above re-reads its
+// 54 neighbours per 4 outputs through L1/L2, which is what bounds it: 14 % of the HBM roofline).  Per frame a thread
+// (row, column, 8 channels) reduces the 9 taps of that frame to the plane maximum of ITS output position, keeps the
+// plane maxima of the last two frames in registers and emits output t-1 as the maximum of three plane maxima.  Compares
+// run on the exact fp32 sums hi + lo; ties resolve to the first tap in (t, y, x) scan order like nn.MaxPool3d; the
+// output planes are the re-split of the winning value (same represented value).
+static constexpr int kPoolTY = 8;
+__global__ void __launch_bounds__(256) maxpool333_smem_kernel(const coclr_pool_t P) {
+  extern __shared__ __align__(16) uint8_t pool_smem[];
+  const int W = P.Wi, H = P.Hi, T = P.Ti;
+  const int WP = W + 2;                                   // padded tile width
+  const int plane_px = (kPoolTY + 2) * WP;                // pixels of one frame tile
+  const uint32_t frame_bytes = (uint32_t)plane_px * 64u;  // hi (32 B / pixel) then lo
+  const int ytiles = (H + kPoolTY - 1) / kPoolTY;
+  const int cslices = P.C >> 4;
+  int blk = blockIdx.x;
+  const int cs = blk % cslices; blk /= cslices;
+  const int yt = blk % ytiles;
+  const int b = blk / ytiles;
+  const int c0 = cs * 16, y0 = yt * kPoolTY;
+  const int tid = threadIdx.x;
+  const int cq = tid & 1, x = (tid >> 1) % W, y = (tid >> 1) / W;     // blockDim = 2 * W * kPoolTY
+  const uint16_t* xh = reinterpret_cast<const uint16_t*>(P.x_hi);
+  const uint16_t* xl = reinterpret_cast<const uint16_t*>(P.x_lo);
+  uint16_t* yh = reinterpret_cast<uint16_t*>(P.y_hi);
+  uint16_t* yl = reinterpret_cast<uint16_t*>(P.y_lo);
+  const uint32_t sbase = smem_u32(pool_smem);
+  // -inf (hi) / 0 (lo) everywhere once: the halo outside the image is never overwritten
+  for (uint32_t i = tid; i < 3u * frame_bytes / 16u; i += blockDim.x) {
+    const uint32_t within = (i * 16u) % frame_bytes;
+    const uint32_t v = within < (uint32_t)plane_px * 32u ? kNegInf2 : 0u;
+    *reinterpret_cast<uint4*>(pool_smem + (size_t)i * 16) = make_uint4(v, v, v, v);
+  }
+  __syncthreads();
+  auto issue_frame = [&](int f) {      // copies of frame f's tile into ring slot f % 3 (in-image pixels only)
+    const uint32_t slot = sbase + (uint32_t)(f % 3) * frame_bytes;
+    const int nchunk = (kPoolTY + 2) * W * 4;          // 16-byte chunks: rows x in-image columns x (hi0, hi1, lo0, lo1)
+    for (int i = tid; i < nchunk; i += blockDim.x) {
+      const int part = i & 3, px = (i >> 2) % W, ry = (i >> 2) / W;
+      const int yi = y0 - 1 + ry;
+      if ((unsigned)yi >= (unsigned)H) continue;
+      const size_t goff = ((((size_t)b * T + f) * H + yi) * W + px) * P.ldx + P.x_coff + c0 + (part & 1) * 8;
+      const uint32_t dst = slot + (part >> 1) * (uint32_t)plane_px * 32u + (uint32_t)(ry * WP + px + 1) * 32u + (part & 1) * 16u;
+      const uint16_t* src = (part >> 1) ? xl : xh;
+      if (src != nullptr) cp_async16(dst, src + goff, 16u);
+    }
+    cp_async_commit();
+  };
+  float v2[8], v1[8];
+  int i2[8], i1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { v2[k] = v1[k] = -INFINITY; i2[k] = i1[k] = 0; }
+  const bool active = (y0 + y) < H;
+  issue_frame(0);
+  for (int f = 0; f <= T; ++f) {
+    if (f + 1 < T) issue_frame(f + 1); else cp_async_commit();    // keep the group count uniform
+    cp_async_wait<1>();
+    __syncthreads();
+    float v0[8];
+    int i0[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v0[k] = -INFINITY; i0[k] = 0; }
+    if (f < T) {
+      const uint8_t* slot = pool_smem + (size_t)(f % 3) * frame_bytes;
+#pragma unroll
+      for (int bb = 0; bb < 3; ++bb) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          const uint32_t px = (uint32_t)((y + bb) * WP + x + cc);
+          const uint4 h = *reinterpret_cast<const uint4*>(slot + px * 32u + cq * 16u);
+          const uint4 l = *reinterpret_cast<const uint4*>(slot + (size_t)plane_px * 32u + px * 32u + cq * 16u);
+          const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float a0 = h2f((uint16_t)(hw[k] & 0xffff)) + h2f((uint16_t)(lw[k] & 0xffff));
+            const float a1 = h2f((uint16_t)(hw[k] >> 16)) + h2f((uint16_t)(lw[k] >> 16));
+            if (a0 > v0[2 * k]) { v0[2 * k] = a0; i0[2 * k] = bb * 3 + cc; }            // ascending (y, x): first max wins
+            if (a1 > v0[2 * k + 1]) { v0[2 * k + 1] = a1; i0[2 * k + 1] = bb * 3 + cc; }
+          }
+        }
+      }
+    }
+    if (f >= 1 && active) {
+      const int to = f - 1;
+      float bv[8];
+      int bt[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        bv[k] = v2[k]; bt[k] = i2[k];                                       // frame to - 1
+        if (v1[k] > bv[k]) { bv[k] = v1[k]; bt[k] = 9 + i1[k]; }            // frame to
+        if (v0[k] > bv[k]) { bv[k] = v0[k]; bt[k] = 18 + i0[k]; }           // frame to + 1
+      }
+      const size_t op = ((((size_t)b * P.To + to) * P.Ho + y0 + y) * P.Wo + x);
+      const size_t oo = op * P.ldy + P.y_coff + c0 + cq * 8;
+      st_pair4<false>(yh, yl, oo, make_float4(bv[0], bv[1], bv[2], bv[3]));
+      st_pair4<false>(yh, yl, oo + 4, make_float4(bv[4], bv[5], bv[6], bv[7]));
+      if (P.y2_hi != nullptr) {
+        st_pair4<true>(reinterpret_cast<uint16_t*>(P.y2_hi), reinterpret_cast<uint16_t*>(P.y2_lo), oo,
+                       make_float4(bv[0], bv[1], bv[2], bv[3]));
+        st_pair4<true>(reinterpret_cast<uint16_t*>(P.y2_hi), reinterpret_cast<uint16_t*>(P.y2_lo), oo + 4,
+                       make_float4(bv[4], bv[5], bv[6], bv[7]));
+      }
+      if (P.idx) {
+        uchar4* ip = reinterpret_cast<uchar4*>(P.idx + op * P.C + c0 + cq * 8);
+        ip[0] = make_uchar4((unsigned char)bt[0], (unsigned char)bt[1], (unsigned char)bt[2], (unsigned char)bt[3]);
+        ip[1] = make_uchar4((unsigned char)bt[4], (unsigned char)bt[5], (unsigned char)bt[6], (unsigned char)bt[7]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v2[k] = v1[k]; i2[k] = i1[k]; v1[k] = v0[k]; i1[k] = i0[k]; }
+    __syncthreads();     // everyone is done with slot f % 3's neighbours before frame f + 2 lands in slot (f + 2) % 3
+  }
+}
+
 // scatter form of the backward: every output element adds its gradient to the one input element that won
 // (fp32 reductions in L2; a window overlaps up to 27 others, so this is ~27x less work than the gather form)
 __global__ void __launch_bounds__(256) maxpool_bwd_scatter_kernel(const coclr_pool_t P) {
@@ -1030,6 +1147,15 @@ extern "C" int coclr_maxpool_fwd(const coclr_pool_t* p, coclr_stream_t stream) {
   const coclr_geom_t& g = p->g;
   if (g.kt == 3 && g.kh == 3 && g.kw == 3 && g.st == 1 && g.sh == 1 && g.sw == 1 && g.pt == 1 && g.ph == 1 &&
       g.pw == 1 && (p->Wo % 4) == 0 && p->Wo == p->Wi && p->Ho == p->Hi && p->To == p->Ti) {
+    static const bool reg_form = getenv("COCLR_POOL333_REG") != nullptr;   // A/B timing: the register-only kernel
+    const int threads = 2 * p->Wi * kPoolTY;
+    if (!reg_form && p->Wi >= 8 && threads <= 256 && p->C % 16 == 0 && p->x_coff % 8 == 0 && p->y_coff % 8 == 0 &&
+        p->ldx % 8 == 0 && p->ldy % 8 == 0) {
+      const size_t smem = (size_t)3 * (kPoolTY + 2) * (p->Wi + 2) * 64;
+      const int grid = p->B * ((p->Hi + kPoolTY - 1) / kPoolTY) * (p->C / 16);
+      maxpool333_smem_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(*p);
+      return LAUNCH_OK();
+    }
     maxpool333_fwd_kernel<<<grid_for(total / 4, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(*p);
     return LAUNCH_OK();
   }
