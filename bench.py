@@ -457,17 +457,31 @@ def main():
                 stage[i % 2].copy_(host_blocks[i % 2], non_blocking=True)
                 ready[i % 2].record(copy_stream)
 
+        # the loss of every step is read back inside the timed region through pinned memory; the read of step i is
+        # completed after step i + 1 has been enqueued (the way a training loop logs), so that the host keeps one
+        # step ahead of the device instead of draining the pipeline with a blocking .item() after every step
+        loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ready = [torch.cuda.Event() for _ in range(2)]
+
         def e2e_loop(n):
             for d in done:
                 d.record()
             prefetch(0)
+            seen = []
             for i in range(n):
                 if i + 1 < n:
                     prefetch(i + 1)
                 torch.cuda.current_stream().wait_event(ready[i % 2])
                 loss = train_step(stage[i % 2])
                 done[i % 2].record()
-                loss.item()                                  # D2H read of the step's result
+                loss_host[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)    # D2H read of the step's result
+                loss_ready[i % 2].record()
+                if i >= 1:
+                    loss_ready[(i - 1) % 2].synchronize()
+                    seen.append(float(loss_host[(i - 1) % 2]))
+            loss_ready[(n - 1) % 2].synchronize()
+            seen.append(float(loss_host[(n - 1) % 2]))
+            return seen
         e2e_loop(max(1, args.warmup // 2))
         barrier()
         t0 = time.perf_counter()

@@ -212,13 +212,16 @@ POOLS = [((1, 3, 3), (1, 2, 2), (0, 1, 1)), ((3, 3, 3), (1, 1, 1), (1, 1, 1)), (
 
 
 @pytest.mark.parametrize("acc", [1, 0], ids=["accumulate", "overwrite"])
-@pytest.mark.parametrize("dims", [(6, 9, 10), (4, 8, 12)], ids=["ragged", "x4"])
+@pytest.mark.parametrize("dims,Cc", [((6, 9, 10), 24), ((4, 8, 12), 24), ((5, 16, 16), 32), ((3, 12, 8), 48), ((2, 64, 64), 16)],
+                         ids=["ragged", "x4", "smem16", "smem8_raggedH", "smem64"])
 @pytest.mark.parametrize("k,s,p", POOLS, ids=["133s2", "333s1", "333s2", "222s2", "generic"])
-def test_maxpool_fwd_bwd(k, s, p, dims, acc, diag):
+def test_maxpool_fwd_bwd(k, s, p, dims, Cc, acc, diag):
+    """The 16-channel-multiple cases on 8/16/64-wide frames take the shared-memory kernels (3x3x3/s1 rolling frame ring,
+    (1,3,3)/s2 tile); the others the register-only kernels."""
     import ctypes as C
     from coclr_b200 import ops, lib as L
     g = torch.Generator(device="cuda").manual_seed(13)
-    B, Cc = 2, 24
+    B = 2
     T, H, W = dims
     x = torch.randn(B, Cc, T, H, W, device="cuda", generator=g)
     x = torch.relu(x)                     # post-ReLU inputs as in the network: many exact ties at 0
