@@ -54,13 +54,22 @@ class STConv3d(nn.Module):
     forward = _holder_forward
 
 
+class SelfGating(nn.Module):
+    """S3D-G feature gating: x * sigmoid(fc(mean_thw(x))) (reference s3dg.py:68-78); nn.Linear's default init."""
+
+    def __init__(self, input_dim):
+        super().__init__()
+        self.fc = nn.Linear(input_dim, input_dim)
+
+    forward = _holder_forward
+
+
 class SepInception(nn.Module):
-    """Four-branch separable Inception block (reference s3dg.py:81-132)."""
+    """Four-branch separable Inception block (reference s3dg.py:81-132); gating=True adds one SelfGating per branch
+    output (:107-112,125-129)."""
 
     def __init__(self, in_planes, out_planes, gating=False):
         super().__init__()
-        if gating:
-            raise NotImplementedError("S3D-G self-gating is outside the accelerated hot path")
         assert isinstance(out_planes, list) and len(out_planes) == 6
         o0, o1a, o1b, o2a, o2b, o3b = out_planes
         self.branch0 = nn.Sequential(BasicConv3d(in_planes, o0, 1, 1))
@@ -69,6 +78,11 @@ class SepInception(nn.Module):
         self.branch3 = nn.Sequential(nn.MaxPool3d((3, 3, 3), 1, 1), BasicConv3d(in_planes, o3b, 1, 1))
         self.out_channels = o0 + o1b + o2b + o3b
         self.gating = gating
+        if gating:
+            self.gating_b0 = SelfGating(o0)
+            self.gating_b1 = SelfGating(o1b)
+            self.gating_b2 = SelfGating(o2b)
+            self.gating_b3 = SelfGating(o3b)
 
     forward = _holder_forward
 
@@ -80,12 +94,12 @@ class S3D(EngineBackbone):
 
     def __init__(self, input_channel=3, gating=False, slow=False, precision="parity"):
         super().__init__()
-        if gating or slow:
-            raise NotImplementedError("gating / slow variants are outside the accelerated hot path")
+        if slow:
+            raise NotImplementedError("the `slow` variant (no temporal stride in the stem) is outside the accelerated path")
         self.gating, self.slow = gating, slow
         self.input_channel = input_channel
         self.precision = precision
-        self._stages = s3d_stages(input_channel)
+        self._stages = s3d_stages(input_channel, gating=gating)
         for stg in self._stages:
             kind, name = stg[0], stg[1]
             if kind == "st":
@@ -96,7 +110,7 @@ class S3D(EngineBackbone):
             elif kind == "pool":
                 mod = nn.MaxPool3d(kernel_size=stg[2], stride=stg[3], padding=stg[4])
             else:
-                mod = SepInception(stg[2], list(stg[3]))
+                mod = SepInception(stg[2], list(stg[3]), gating=gating)
             setattr(self, name, mod)
             if kind == "st" and name == "Conv_1a":
                 self.block1 = nn.Sequential(mod)

@@ -27,8 +27,8 @@ CFG = dict(network="s3d", dim=128, K=2048, m=0.999, T=0.07, B=32, seq_len=32, im
 # bounded CPU sample of the workload (reference arm and cpu_baseline leg): 4 clip pairs of 16 frames = 4 of the benchmark's
 # 32-frame clips per step, ~1 s per step on 16 host cores -> ~10 s for the default 8 timed steps
 CPU_SAMPLE_BATCH, CPU_SAMPLE_T = 4, 16
-GFLOP_PER_PAIR = {"s3d": 91.46, "r50": 231.67}  # q fwd+dgrad+wgrad, k fwd (conv MACs x2), one clip pair
-NET_NAME = {"s3d": "S3D", "r50": "R2D3D-50"}
+GFLOP_PER_PAIR = {"s3d": 91.46, "s3dg": 91.46, "r50": 231.67}  # q fwd+dgrad+wgrad, k fwd (conv MACs x2), one clip pair
+NET_NAME = {"s3d": "S3D", "s3dg": "S3D-G", "r50": "R2D3D-50"}
 
 
 def parse():
@@ -38,8 +38,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="coclr_b200", choices=["coclr_b200", "reference"])
     ap.add_argument("--precision", default="parity", choices=["parity", "mixed", "fast"])
-    ap.add_argument("--net", default=CFG["network"], choices=["s3d", "r50"],
-                    help="backbone: s3d = BASELINE.json configs 1-4 (headline), r50 = config 5 (ResNet2d3d-50)")
+    ap.add_argument("--net", default=CFG["network"], choices=["s3d", "s3dg", "r50"],
+                    help="backbone: s3d = BASELINE.json configs 1-4 (headline), r50 = config 5 (ResNet2d3d-50), "
+                         "s3dg = S3D with feature gating (select_backbone.py:8-9; same conv FLOPs)")
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--seq_len", type=int, default=CFG["seq_len"])
     ap.add_argument("--moco-k", type=int, default=CFG["K"], help="queue length: 2048 = config 2 (headline), 16384 = config 3")

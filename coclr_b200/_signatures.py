@@ -34,6 +34,12 @@ EXPORTS = {
     "coclr_nce_logits_ce": (I, [P, P, P, F, I, I, I, P, P, P, P, P]),
     "coclr_nce_logits_bwd": (I, [P, P, P, F, I, I, I, P, P]),
     "coclr_mask_topk": (I, [P, P, P, P, I, I, I, I, P, P]),
+    "coclr_gate_mean": (I, [P, P, I, I, I, I, I, P, P]),
+    "coclr_gate_fc": (I, [P, P, P, P, I, I, I, I, P]),
+    "coclr_gate_apply": (I, [P, P, I, I, I, I, I, P, P]),
+    "coclr_gate_bwd_reduce": (I, [P, I, P, P, I, P, I, I, I, I, P, P]),
+    "coclr_gate_fc_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, P]),
+    "coclr_gate_bwd_apply": (I, [P, I, P, P, I, I, I, P]),
 }
 
 

@@ -45,6 +45,7 @@ class TensorSpec:
         self.bn_members = []   # (bn module name, coff, C) in channel order
         self.relu = 1 if pending else 0
         self.residual = None   # TensorSpec added before the ReLU (ResNet bottleneck output)
+        self.gates = []        # S3D-G: (SelfGating module name, coff, C) per branch slice of a SepInception output
 
 
 class ConvSpec:
@@ -157,8 +158,8 @@ class Graph:
                 _, name, inplanes, planes, stride, is3d, has_ds = stg
                 x = self._bottleneck(pre + name, x, inplanes, planes, stride, is3d, has_ds)
             elif kind == "mixed":
-                _, name, cin, planes = stg
-                x = self._mixed(pre + name, x, cin, planes)
+                name, cin, planes = stg[1:4]
+                x = self._mixed(pre + name, x, cin, planes, gating=len(stg) > 4 and bool(stg[4]))
             else:
                 raise ValueError(kind)
         self.backbone_out = x
@@ -210,9 +211,12 @@ class Graph:
         self.items.append(("pool", PoolSpec(name, x, y, k, s, p)))
         return y
 
-    def _mixed(self, name, x, cin, planes):
+    def _mixed(self, name, x, cin, planes, gating=False):
         o0, o1a, o1b, o2a, o2b, o3b = planes
         cat = self._tensor(name, o0 + o1b + o2b + o3b, self._same(x))
+        if gating:   # SepInception(gating=True): one SelfGating per branch output (backbone/s3dg.py:107-112,125-129)
+            cat.gates = [(name + ".gating_b0", 0, o0), (name + ".gating_b1", o0, o1b),
+                         (name + ".gating_b2", o0 + o1b, o2b), (name + ".gating_b3", o0 + o1b + o2b, o3b)]
         one = ((1, 1, 1), (1, 1, 1), (0, 0, 0))
         if self.fuse_b12:
             t12 = self._tensor(name + ".b12a", o1a + o2a, self._same(x))
@@ -308,6 +312,10 @@ class Graph:
                     out.append((nm + ".weight", (c,)))
                 for nm, _, c in it.bn_members:
                     out.append((nm + ".bias", (c,)))
+        for kind, it in self.items:
+            if kind == "bn":
+                for nm, _, c in it.gates:      # nn.Linear(c, c) of a SelfGating
+                    out += [(nm + ".fc.weight", (c, c)), (nm + ".fc.bias", (c,))]
         if self.head_dim is not None:
             fs = self.feature_size
             out += [("2.weight", (fs, fs, 1, 1, 1)), ("2.bias", (fs,)),
@@ -402,7 +410,7 @@ class ParamStore:
 # ---------------------------------------------------------------------------------------------
 class _Act:
     __slots__ = ("spec", "dims", "data", "pl", "plw", "grad", "dy", "scale", "shift", "mean", "rstd", "ssum", "ssq", "idx",
-                 "bsums", "grad_written", "M", "dy_scale", "bamax")
+                 "bsums", "grad_written", "M", "dy_scale", "bamax", "gmean", "gate", "dgate", "dmean")
 
 
 class Plan:
@@ -441,6 +449,7 @@ class Plan:
             a.pl = ops.Planes(shape, fbf, dev, lo=fnp > 1, zero=padded)   # what every forward consumer reads
             a.plw = a.pl if with_backward else None     # ... and the weight-gradient GEMM (same 16-bit format as dY)
             a.data = a.grad = a.dy = a.idx = a.bsums = a.dy_scale = a.bamax = None
+            a.gmean = a.gate = a.dgate = a.dmean = None
             a.grad_written = False
             if t.pending:
                 a.data = torch.empty(shape, dtype=torch.float32, device=dev)   # raw conv output (pre-BN)
@@ -533,6 +542,21 @@ class Plan:
                 # BatchNorm finalize is fused into the apply+split launch
                 res = acts[it.residual.index].pl if it.residual is not None else None
                 self.fwd.append(split_op(a.data, a.pl, a.M, it.C, None, None, it.relu, a.plw, bn=bf, res=res))
+                if it.gates:
+                    # S3D-G feature gating of the block output: the planes written above are scaled in place by
+                    # sigmoid(fc(mean_thw)) per clip and channel (csrc/gating.cu)
+                    assert a.plw is None or a.plw is a.pl
+                    Pn = a.dims[0] * a.dims[1] * a.dims[2]
+                    a.gmean = torch.empty(B, it.C, dtype=torch.float32, device=dev)
+                    a.gate = torch.empty(B, it.C, dtype=torch.float32, device=dev)
+                    self.fwd.append((lib.coclr_gate_mean, (L.dptr(a.pl.hi), L.dptr(a.pl.lo), a.pl.bf16, a.pl.ld, B, Pn,
+                                                           it.C, L.dptr(a.gmean))))
+                    for nm, coff, c in it.gates:
+                        self.fwd.append((lib.coclr_gate_fc, (L.dptr(a.gmean), L.dptr(st.view(nm + ".fc.weight")),
+                                                             L.dptr(st.view(nm + ".fc.bias")), L.dptr(a.gate), B, it.C,
+                                                             coff, c)))
+                    self.fwd.append((lib.coclr_gate_apply, (L.dptr(a.pl.hi), L.dptr(a.pl.lo), a.pl.bf16, a.pl.ld, B, Pn,
+                                                            it.C, L.dptr(a.gate))))
             for j in range(n_before, len(self.fwd)):     # tag the launches of this item with its lane / fork / join
                 self.fwd_lane[j] = (g.item_lane[item_i], g.item_flag[item_i] if j == n_before else 0)
         # ---- head ----
@@ -622,6 +646,20 @@ class Plan:
             if not a.grad_written:
                 raise RuntimeError("tensor %s never receives a gradient" % t.name)
             if t.pending:
+                if t.gates:
+                    # a.grad holds d/d(gated output); turn it into d/d(un-gated activation) and emit the fc gradients
+                    Pn = a.dims[0] * a.dims[1] * a.dims[2]
+                    a.dgate = torch.empty(B, t.C, dtype=torch.float32, device=dev)
+                    a.dmean = torch.empty(B, t.C, dtype=torch.float32, device=dev)
+                    bw.append((lib.coclr_gate_bwd_reduce, (L.dptr(a.data), t.C, L.dptr(a.scale), L.dptr(a.shift), t.relu,
+                                                           L.dptr(a.grad), t.C, B, Pn, t.C, L.dptr(a.dgate))))
+                    for nm, coff, c in t.gates:
+                        bw.append((lib.coclr_gate_fc_bwd, (L.dptr(a.dgate), L.dptr(a.gate), L.dptr(a.gmean),
+                                                           L.dptr(st.view(nm + ".fc.weight")),
+                                                           L.dptr(st.view(nm + ".fc.weight", grad=True)),
+                                                           L.dptr(st.view(nm + ".fc.bias", grad=True)), L.dptr(a.dmean),
+                                                           B, t.C, coff, c)))
+                    bw.append((lib.coclr_gate_bwd_apply, (L.dptr(a.grad), t.C, L.dptr(a.gate), L.dptr(a.dmean), B, Pn, t.C)))
                 a.bsums = torch.zeros(2 * t.C, dtype=torch.float64, device=dev)
                 a.bamax = torch.zeros(2 * t.C, dtype=torch.float32, device=dev)
                 first = t.bn_members[0][0]
@@ -689,6 +727,8 @@ class Plan:
                             L.dptr(a.grad), L.dptr(sa.grad), int(grad_seen(sa)))
                 self.keep.append(pl)
                 bw.append((lib.coclr_maxpool_bwd, (C.byref(pl),)))
+        if any(t.gates for t in g.tensors):
+            self.bwd_split = None   # gating parameters sit behind the BatchNorm region: one all-reduce at the end
 
 
 class EncoderEngine:

@@ -118,7 +118,7 @@ def load():
 
 
 LAUNCHES = 0  # kernels of this library launched so far in this process (bench.py reports the per-step count)
-KERNELS_PER_CALL = {"coclr_bn_bwd": 2, "coclr_l2norm_bwd": 2, "coclr_conv_packed_bytes": 0}
+KERNELS_PER_CALL = {"coclr_bn_bwd": 2, "coclr_l2norm_bwd": 2, "coclr_conv_packed_bytes": 0, "coclr_gate_fc_bwd": 2}
 
 
 def check(rc, what):

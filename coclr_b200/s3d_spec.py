@@ -19,12 +19,12 @@ S3D_INCEPTION = {
 }
 
 
-def s3d_stages(first_channel=3):
+def s3d_stages(first_channel=3, gating=False):
     """Ordered stage list. Entries:
        ("st", name, cin, cout, k, spatial_stride, temporal_stride, pad)   separable conv (STConv3d)
        ("basic", name, cin, cout)                                          1x1x1 conv (BasicConv3d)
        ("pool", name, kernel, stride, padding)                             nn.MaxPool3d
-       ("mixed", name, cin, planes)                                        SepInception
+       ("mixed", name, cin, planes[, gating])                              SepInception (gating: S3D-G, s3dg.py:68-78)
     `block` membership (reference registers blockN aliases) is in S3D_BLOCKS."""
     st = [("st", "Conv_1a", first_channel, 64, 7, 2, 2, 3),
           ("pool", "MaxPool_2a", (1, 3, 3), (1, 2, 2), (0, 1, 1)),
@@ -32,13 +32,13 @@ def s3d_stages(first_channel=3):
           ("st", "Conv_2c", 64, 192, 3, 1, 1, 1),
           ("pool", "MaxPool_3a", (1, 3, 3), (1, 2, 2), (0, 1, 1))]
     for n in ("Mixed_3b", "Mixed_3c"):
-        st.append(("mixed", n) + S3D_INCEPTION[n])
+        st.append(("mixed", n) + S3D_INCEPTION[n] + (bool(gating),))
     st.append(("pool", "MaxPool_4a", (3, 3, 3), (2, 2, 2), (1, 1, 1)))
     for n in ("Mixed_4b", "Mixed_4c", "Mixed_4d", "Mixed_4e", "Mixed_4f"):
-        st.append(("mixed", n) + S3D_INCEPTION[n])
+        st.append(("mixed", n) + S3D_INCEPTION[n] + (bool(gating),))
     st.append(("pool", "MaxPool_5a", (2, 2, 2), (2, 2, 2), (0, 0, 0)))
     for n in ("Mixed_5b", "Mixed_5c"):
-        st.append(("mixed", n) + S3D_INCEPTION[n])
+        st.append(("mixed", n) + S3D_INCEPTION[n] + (bool(gating),))
     return st
 
 

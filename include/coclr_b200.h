@@ -311,6 +311,27 @@ int coclr_nce_logits_bwd(const float* dlogits, const float* k, const float* queu
 int coclr_mask_topk(const float* kf, const float* queue_second, const long* k_vsource, const long* queue_vname, int B, int D,
                     int K, int topk, unsigned char* mask, coclr_stream_t stream);
 
+/* ---- S3D-G feature gating, SelfGating (backbone/s3dg.py:68-78) applied to the branch outputs of a SepInception
+ * (:125-129): out[b, c, thw] = sigmoid(fc(mean_thw(a[b])))[c] * a[b, c, thw].  The four branches write channel slices
+ * of ONE channels-last concat buffer [B, P = T*H*W, C] (16-bit hi/lo planes, row stride ld); the four nn.Linear layers
+ * are the diagonal blocks (coff, n) of the fc step: call coclr_gate_fc / coclr_gate_fc_bwd once per member.
+ *   forward : coclr_gate_mean -> coclr_gate_fc (x members) -> coclr_gate_apply (planes scaled in place)
+ *   backward: coclr_gate_bwd_reduce (dgate[b, c] = sum_thw dout * a, a = act(y * scale + shift) recomputed from the raw
+ *             conv output y and the BatchNorm affine) -> coclr_gate_fc_bwd (x members; dW [n, n] row-major like
+ *             nn.Linear.weight, dbias [n], dmean) -> coclr_gate_bwd_apply (dout <- gate * dout + dmean / P, in place:
+ *             the gradient w.r.t. the un-gated activation, which coclr_bn_bwd then consumes unchanged).
+ * mean / gate / dgate / dmean: fp32 [B, C]. */
+int coclr_gate_mean(const void* x_hi, const void* x_lo, int bf16 /* plane format */, int ld, int B, int P, int C, float* mean,
+                    coclr_stream_t stream);
+int coclr_gate_fc(const float* mean, const float* W, const float* bias, float* gate, int B, int C, int coff, int n,
+                  coclr_stream_t stream);
+int coclr_gate_apply(void* x_hi, void* x_lo, int bf16, int ld, int B, int P, int C, const float* gate, coclr_stream_t stream);
+int coclr_gate_bwd_reduce(const float* y, int ldy, const float* scale, const float* shift, int relu, const float* dout, int ldd,
+                          int B, int P, int C, float* dgate, coclr_stream_t stream);
+int coclr_gate_fc_bwd(const float* dgate, const float* gate, const float* mean, const float* W, float* dW, float* dbias,
+                      float* dmean, int B /* <= 256 */, int C, int coff, int n, coclr_stream_t stream);
+int coclr_gate_bwd_apply(float* dout, int ldd, const float* gate, const float* dmean, int B, int P, int C, coclr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

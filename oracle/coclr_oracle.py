@@ -61,8 +61,17 @@ def st_conv(sd, pre, x, k, stride, t_stride, pad, training):
     return _bn_relu(sd, pre + ".bn2", x, training)
 
 
+def self_gating(sd, pre, x):
+    """SelfGating ("feature gating as used in S3D-G"): sigmoid(fc(mean over T,H,W)) scales every channel of every clip;
+    backbone/s3dg.py:68-78."""
+    avg = torch.mean(x, dim=[2, 3, 4])                                              # :75
+    w = torch.sigmoid(F.linear(avg, sd[pre + ".fc.weight"], sd[pre + ".fc.bias"]))  # :76-77
+    return w[:, :, None, None, None] * x                                            # :78
+
+
 def sep_inception(sd, pre, x, training):
-    """SepInception: 4 branches concatenated on channels; backbone/s3dg.py:81-132."""
+    """SepInception: 4 branches concatenated on channels; backbone/s3dg.py:81-132.  With gating (network 's3dg',
+    select_backbone.py:8-9; recognised from the state keys) each branch output goes through its SelfGating (:125-129)."""
     x0 = basic_conv(sd, pre + ".branch0.0", x, training)
     x1 = basic_conv(sd, pre + ".branch1.0", x, training)
     x1 = st_conv(sd, pre + ".branch1.1", x1, 3, 1, 1, 1, training)
@@ -70,6 +79,11 @@ def sep_inception(sd, pre, x, training):
     x2 = st_conv(sd, pre + ".branch2.1", x2, 3, 1, 1, 1, training)
     x3 = F.max_pool3d(x, kernel_size=(3, 3, 3), stride=1, padding=1)
     x3 = basic_conv(sd, pre + ".branch3.1", x3, training)
+    if (pre + ".gating_b0.fc.weight") in sd:                                        # :124
+        x0 = self_gating(sd, pre + ".gating_b0", x0)
+        x1 = self_gating(sd, pre + ".gating_b1", x1)
+        x2 = self_gating(sd, pre + ".gating_b2", x2)
+        x3 = self_gating(sd, pre + ".gating_b3", x3)
     return torch.cat((x0, x1, x2, x3), 1)
 
 
@@ -284,8 +298,8 @@ def adam_step(params, grads, state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weigh
 # ---------------------------------------------------------------------------------------------
 # shapes + deterministic synthetic state (shared by the golden generator and the tests)
 # ---------------------------------------------------------------------------------------------
-def s3d_shapes(pre, first_channel=3):
-    """{key: shape} of an S3D backbone under prefix `pre` (parameters and BN buffers)."""
+def s3d_shapes(pre, first_channel=3, gating=False):
+    """{key: shape} of an S3D backbone under prefix `pre` (parameters and BN buffers); gating: the S3D-G variant."""
     sh = {}
 
     def bn(p, c):
@@ -315,14 +329,18 @@ def s3d_shapes(pre, first_channel=3):
         basic(pre + name + ".branch2.0", cin, o2a)
         st(pre + name + ".branch2.1", o2a, o2b, 3)
         basic(pre + name + ".branch3.1", cin, o3b)
+        if gating:                                                                   # s3dg.py:107-112
+            for i, c in enumerate((o0, o1b, o2b, o3b)):
+                sh["%s%s.gating_b%d.fc.weight" % (pre, name, i)] = (c, c)
+                sh["%s%s.gating_b%d.fc.bias" % (pre, name, i)] = (c,)
     return sh
 
 
 def infonce_shapes(dim=128, K=2048, feature_size=None, network="s3d"):
     sh = {}
-    feature_size = feature_size or {"s3d": 1024, "r50": 2048}[network]
+    feature_size = feature_size or {"s3d": 1024, "s3dg": 1024, "r50": 2048}[network]
     for enc in ("encoder_q.", "encoder_k."):
-        sh.update(s3d_shapes(enc + "0.") if network == "s3d" else r50_shapes(enc + "0."))
+        sh.update(r50_shapes(enc + "0.") if network == "r50" else s3d_shapes(enc + "0.", gating=network == "s3dg"))
         sh[enc + "2.weight"] = (feature_size, feature_size, 1, 1, 1)
         sh[enc + "2.bias"] = (feature_size,)
         sh[enc + "4.weight"] = (dim, feature_size, 1, 1, 1)
@@ -355,6 +373,8 @@ def synth_state(shapes, seed=0, ptr=0, k_delta=0.02):
             sd[k] = torch.randn(s, generator=g) * 0.1
         elif k.endswith(".bias"):
             sd[k] = torch.randn(s, generator=g) * 0.05
+        elif len(s) == 2:  # nn.Linear weight of a SelfGating: gates spread over (0.2, 0.8) instead of all ~0.5
+            sd[k] = torch.randn(s, generator=g) * (4.0 / s[1]) ** 0.5
         else:  # conv weight
             fan_in = s[1] * s[2] * s[3] * s[4]
             sd[k] = torch.randn(s, generator=g) * (2.0 / fan_in) ** 0.5

@@ -1,4 +1,4 @@
-"""Generates tests/golden/infonce_cfg1.npz (and, with the argument `r50`, infonce_r50.npz) by running the UNMODIFIED reference (TengdaHan/CoCLR at
+"""Generates tests/golden/infonce_cfg1.npz (and, with the argument `r50` / `s3dg`, infonce_r50.npz / infonce_s3dg.npz) by running the UNMODIFIED reference (TengdaHan/CoCLR at
 /root/reference, model/pretrain.py InfoNCE) on BASELINE.json config 1 (S3D, moco-k=128, bs=4,
 seq_len=8, 128x128, CPU) from the deterministic synthetic state of oracle.coclr_oracle.synth_state.
 
@@ -74,6 +74,15 @@ GRAD_KEYS_R50 = ["encoder_q.0.conv1.weight", "encoder_q.0.bn1.weight", "encoder_
 R50_CFG = dict(K=128, B=4, T=8, HW=64, ptr=16)     # BASELINE.json config 5 (--net r50) at a CPU-sized shape
 
 
+# S3D-G (`--net s3dg`, select_backbone.py:8-9: S3D with a SelfGating on every SepInception branch output)
+GRAD_KEYS_S3DG = ["encoder_q.0.Conv_1a.conv1.weight", "encoder_q.0.Conv_2c.conv2.weight",
+                  "encoder_q.0.Mixed_3b.gating_b1.fc.weight", "encoder_q.0.Mixed_3b.gating_b1.fc.bias",
+                  "encoder_q.0.Mixed_3c.branch1.1.conv1.weight", "encoder_q.0.Mixed_4c.gating_b0.fc.weight",
+                  "encoder_q.0.Mixed_4f.branch3.1.bn.bias", "encoder_q.0.Mixed_5c.gating_b3.fc.bias",
+                  "encoder_q.0.Mixed_5c.branch1.1.conv2.weight", "encoder_q.2.weight", "encoder_q.4.bias"]
+S3DG_CFG = dict(K=128, B=4, T=8, HW=128, ptr=16)     # config 1 shape (the 64x64 r50 shape leaves Mixed_5 BatchNorms 16 samples)
+
+
 def run_reference(K=128, B=4, T=8, ptr=16, threads=8, network="s3d", HW=128):
     import torch.distributed as dist
     InfoNCE = import_reference().InfoNCE  # the unmodified reference
@@ -100,6 +109,12 @@ def run_reference(K=128, B=4, T=8, ptr=16, threads=8, network="s3d", HW=128):
     if network == "s3d":
         for k in GRAD_KEYS:
             out["grad/" + k] = named[k].grad.numpy().copy()
+    if network == "s3dg":
+        for k in GRAD_KEYS_S3DG:
+            out["grad/" + k], nrm = compact(named[k].grad.numpy())
+            if nrm is not None:
+                out["gradnorm/" + k] = nrm
+        out["ema/encoder_k.0.Mixed_4b.gating_b2.fc.weight"] = named["encoder_k.0.Mixed_4b.gating_b2.fc.weight"].detach().numpy().copy()
     if network == "r50":
         for k in GRAD_KEYS_R50:
             out["grad/" + k], nrm = compact(named[k].grad.numpy())
@@ -117,7 +132,10 @@ def run_reference(K=128, B=4, T=8, ptr=16, threads=8, network="s3d", HW=128):
 
 
 if __name__ == "__main__":
-    if "r50" in sys.argv[1:]:
+    if "s3dg" in sys.argv[1:]:
+        out, _ = run_reference(network="s3dg", **S3DG_CFG)
+        np.savez_compressed(os.path.join(HERE, "infonce_s3dg.npz"), **out)
+    elif "r50" in sys.argv[1:]:
         out, _ = run_reference(network="r50", **R50_CFG)
         np.savez_compressed(os.path.join(HERE, "infonce_r50.npz"), **out)
     else:

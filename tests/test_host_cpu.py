@@ -66,6 +66,52 @@ def test_select_backbone_contract():
     assert p == {"feature_size": 1024}
     with pytest.raises(NotImplementedError):
         select_backbone("nope")
+    mg, pg = select_backbone("s3dg")      # S3D with feature gating (reference select_backbone.py:8-9)
+    assert pg == {"feature_size": 1024} and mg.gating
+    extra = set(dict(mg.named_parameters())) - set(dict(m.named_parameters()))
+    assert len(extra) == 2 * 4 * 9 and all(".gating_b" in k for k in extra)   # (weight, bias) x 4 branches x 9 blocks
+    assert tuple(mg.Mixed_4b.gating_b1.fc.weight.shape) == (208, 208)
+
+
+def test_s3dg_graph_and_plan_dry_run():
+    """S3D-G: parameter layout equals the reference's (through the oracle's shape table, itself checked against the
+    reference's state_dict in tests/test_oracle.py), and the launch plan gates every SepInception output: forward
+    mean -> 4 fc -> apply after the block's BatchNorm, backward reduce -> 4 fc_bwd -> apply before its BatchNorm backward."""
+    from coclr_b200 import lib as L
+    from coclr_b200.engine import Graph, ParamStore, EncoderEngine
+    from coclr_b200.s3d_spec import s3d_stages
+    from oracle import coclr_oracle as O
+    g = Graph(s3d_stages(3, gating=True), 3, head_dim=128, bb_prefix="0.")
+    lay = dict(g.param_layout())
+    shapes = {k[len("encoder_q."):]: tuple(v) for k, v in O.infonce_shapes(128, 128, network="s3dg").items()
+              if k.startswith("encoder_q.") and (k.endswith(".weight") or k.endswith(".bias"))}
+    assert set(lay) == set(shapes) and all(tuple(lay[k]) == s for k, s in shapes.items())
+    L.DRY_RUN = True
+    try:
+        st = ParamStore(g, torch.device("cpu"))
+        eng = EncoderEngine(st, g, "parity")
+        p = eng.plan(2, 8, 64, 64, True, True)
+        fw = [fn.__name__ for fn, _ in p.fwd]
+        assert fw.count("coclr_gate_mean") == 9 and fw.count("coclr_gate_fc") == 36 and fw.count("coclr_gate_apply") == 9
+        for i, n in enumerate(fw):
+            if n == "coclr_gate_mean":
+                assert fw[i - 1] == "coclr_affine_split" and fw[i + 1:i + 6] == ["coclr_gate_fc"] * 4 + ["coclr_gate_apply"]
+        bw = [fn.__name__ for fn, _ in p.bwd]
+        assert bw.count("coclr_gate_bwd_reduce") == 9 and bw.count("coclr_gate_fc_bwd") == 36
+        for i, n in enumerate(bw):
+            if n == "coclr_gate_bwd_reduce":
+                assert bw[i + 1:i + 7] == ["coclr_gate_fc_bwd"] * 4 + ["coclr_gate_bwd_apply", "coclr_bn_bwd"]
+        assert p.bwd_split is None       # the gating parameters are reduced with everything else at the end
+        # every gating parameter's gradient is written by exactly one launch
+        base = st.grad.data_ptr()
+        offs = sorted((a[4].value - base) // 4 for fn, a in p.bwd if fn.__name__ == "coclr_gate_fc_bwd")
+        want = sorted(st.offsets[k][0] for k in st.offsets if k.endswith(".fc.weight"))
+        assert offs == want and len(set(offs)) == 36
+        # the forward-only plan (key encoder) gates too
+        pk = eng.plan(2, 8, 64, 64, True, False)
+        assert [fn.__name__ for fn, _ in pk.fwd].count("coclr_gate_apply") == 9
+    finally:
+        L.DRY_RUN = False
 
 
 def test_graph_covers_reference_parameters():

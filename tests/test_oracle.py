@@ -160,3 +160,55 @@ def test_oracle_adam_is_torch_optim_adam():
         O.adam_step(mine, {str(i): gr for i, gr in enumerate(grads)}, state, lr=1e-3, weight_decay=1e-5)
         for i, p in enumerate(ref_params):
             assert torch.equal(mine[str(i)], p.detach()), (step, i)
+
+
+# ---- s3dg (S3D with feature gating, `--net s3dg`; backbone/s3dg.py:68-78,107-112,125-129) ---------
+GOLD_S3DG = os.path.join(ROOT, "tests", "golden", "infonce_s3dg.npz")
+
+
+def _oracle_step_s3dg():
+    c = MG.S3DG_CFG
+    sd = O.synth_state(O.infonce_shapes(128, c["K"], network="s3dg"), seed=0, ptr=c["ptr"])
+    for k in O.param_keys(sd, "encoder_q."):
+        sd[k].requires_grad_(True)
+    block = MG.make_inputs_shifted(c["B"], c["T"], c["HW"])
+    torch.manual_seed(77)
+    idx = torch.randperm(c["B"])
+    logits, labels = O.infonce_forward(sd, [block], idx)
+    loss = O.infonce_loss(logits[0], labels)
+    loss.backward()
+    return sd, logits[0], loss
+
+
+def test_oracle_s3dg_matches_golden():
+    gold = np.load(GOLD_S3DG)
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    sd, logits, loss = _oracle_step_s3dg()
+    assert logits.shape == (4, 129)
+    assert _rel(logits.detach().numpy(), gold["logits"]) < 2e-4
+    assert _rel(sd["queue"].numpy(), gold["queue"]) < 2e-4
+    assert int(sd["queue_ptr"]) == int(gold["queue_ptr"][0]) == 20
+    assert _rel(sd["encoder_k.0.Mixed_4b.gating_b2.fc.weight"].detach().numpy(),
+                gold["ema/encoder_k.0.Mixed_4b.gating_b2.fc.weight"]) < 1e-6
+    for k in MG.GRAD_KEYS_S3DG:
+        got, _ = MG.compact(sd[k].grad.numpy())
+        assert _rel(got, gold["grad/" + k]) < 5e-2, k
+    # 9 SepInception blocks x 4 SelfGating x (weight, bias) on top of S3D's 235 tensors
+    assert len(O.param_keys(sd, "encoder_q.")) == 235 + 72
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference not mounted")
+def test_oracle_s3dg_bitwise_vs_reference():
+    torch.set_num_threads(8)
+    out, model = MG.run_reference(threads=8, network="s3dg", **MG.S3DG_CFG)
+    sd, logits, loss = _oracle_step_s3dg()
+    assert np.array_equal(logits.detach().numpy(), out["logits"])
+    assert loss.item() == float(out["loss"])
+    assert np.array_equal(sd["queue"].numpy(), out["queue"])
+    named = dict(model.named_parameters())
+    for k in MG.GRAD_KEYS_S3DG:
+        assert _rel(sd[k].grad.numpy(), named[k].grad.numpy()) < 1e-6, k
+    msd = model.state_dict()
+    assert set(msd.keys()) == set(O.with_aliases(sd).keys())
+    for k, v in sd.items():
+        assert _rel(v.detach().numpy(), msd[k].numpy()) < 1e-6, k
