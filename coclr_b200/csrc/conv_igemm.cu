@@ -530,6 +530,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
   const int c_tiles = (P.Cout + 127) / 128;
   const WgradSmemLayout L = wgrad_smem_layout(BNk, kNPass);
   const uint32_t nstages = L.stages;
+  // Cout <= 64 in split-precision mode: the hi and the lo plane of dY are the two 64-row halves of ONE M = 128 operand
+  // ([dY_hi; dY_lo] x A_hi, then x A_lo: 2 instructions per K step instead of 3 on a half-empty tile, and the lo x lo
+  // term comes for free); lanes 64..127 hold the dY_lo products of channels 0..63 and are added by the epilogue
+  const bool stack_m = kLo && P.Cout <= 64;
 
   // work item: (split, c_tile, k_tile)
   int w = blockIdx.x;
@@ -596,11 +600,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
       mbar_wait(&empty_bar[stage], phase ^ 1u);
       const uint32_t s_dy = smem_base + stage * L.stage_bytes;
       const uint32_t s_a = s_dy + (kLo ? 2u : 1u) * L.dy_bytes;
-      // dY: 2 blocks of 64 output channels
+      // dY: 2 blocks of 64 output channels (stacked mode: block 0 = hi plane, block 1 = lo plane of channels 0..63)
+      if (stack_m) {
+        gather_block_async<kLo, 2>(P.dy, ident, P.dy.C, tp_dy[0], ck, r0, qb, qt, qy, qx, s_dy, s_dy + kWgPx * 128);
+      } else {
 #pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {
-        gather_block_async<kLo, 2>(P.dy, ident, P.dy.C, tp_dy[blk], ck, r0, qb, qt, qy, qx,
-                                   s_dy + blk * (kWgPx * 128), s_dy + L.dy_bytes + blk * (kWgPx * 128));
+        for (int blk = 0; blk < 2; ++blk) {
+          gather_block_async<kLo, 2>(P.dy, ident, P.dy.C, tp_dy[blk], ck, r0, qb, qt, qy, qx,
+                                     s_dy + blk * (kWgPx * 128), s_dy + L.dy_bytes + blk * (kWgPx * 128));
+        }
       }
 #pragma unroll
       for (int blk = 0; blk < 4; ++blk) {
@@ -629,8 +637,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
           const uint64_t b_lo = make_smem_desc(s_a + L.a_bytes, kWgPx * 128, 1024);
 #pragma unroll
           for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_base, a_hi + 128 * k, b_lo + 128 * k, idesc, (ch | k) != 0);
+          if (!stack_m) {
 #pragma unroll
-          for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_base, a_lo + 128 * k, b_hi + 128 * k, idesc, 1u);
+            for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_base, a_lo + 128 * k, b_hi + 128 * k, idesc, 1u);
+          }
 #pragma unroll
           for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_base, a_hi + 128 * k, b_hi + 128 * k, idesc, 1u);
         } else {
@@ -647,7 +657,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const coclr_wgr
     if (nch > 0) {
       mbar_wait(&tfull_bar[0], 0);
       tc_fence_after();
-      const int n = c_tile * 128 + warp * 32 + lane;  // output channel of this thread
+      int n = c_tile * 128 + warp * 32 + lane;  // output channel of this thread
+      if (stack_m) n &= 63;
       const float os = P.out_scale != nullptr ? __ldg(P.out_scale) : 1.f;
       for (int c0 = 0; c0 < BNk; c0 += 32) {
         uint32_t v[32];
