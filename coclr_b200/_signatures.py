@@ -14,6 +14,9 @@ EXPORTS = {
     "coclr_conv_tma_plan": (I, [P, C.POINTER(I)]),
     "coclr_set_conv_tma": (None, [I]),
     "coclr_conv_wgrad": (I, [P, P]),
+    "coclr_set_wgrad_tma": (None, [I]),
+    "coclr_wgrad_tma_plan": (I, [P, C.POINTER(I)]),
+    "coclr_wgrad_ws_floats": (LG, [P]),
     "coclr_pack_weights": (I, [P, P]),
     "coclr_pack_weights_batch": (I, [P, P, I, I, P]),
     "coclr_affine_split": (I, [P, I, P]),

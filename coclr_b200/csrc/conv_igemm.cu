@@ -885,5 +885,8 @@ extern "C" int coclr_conv_wgrad(const coclr_wgrad_t* p, coclr_stream_t stream) {
       (long long)p->B * p->dy.T * p->dy.H * p->dy.W >= (1ll << 31))
     return COCLR_E_ARG;  // 32-bit pixel indices
   cudaStream_t s = (cudaStream_t)stream;
+  // TMA-staged kernel first (wgrad_tma.cu: stride-1 "same" convolutions); everything else on the gather kernel
+  const int rc = coclr::wgrad_tma_try(*p, s);
+  if (rc <= 0) return rc;
   return p->npass > 1 ? launch_wgrad<3>(*p, s) : launch_wgrad<1>(*p, s);
 }

@@ -495,14 +495,6 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 // ------------------------------------------------------------------------------------------------
 // host side: applicability, tile plan, tensor maps
 // ------------------------------------------------------------------------------------------------
-struct MapSpec {
-  void* base[2];
-  uint64_t dims[5];
-  uint64_t strides[4];   // bytes, dims 1..4
-  uint32_t box[5];
-  int elem_bytes;
-};
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -521,7 +513,7 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static bool encode_map(CUtensorMap* m, const MapSpec& s, int which, int rank = 5, bool swizzle = true) {
+bool encode_map(CUtensorMap* m, const MapSpec& s, int which, int rank, bool swizzle) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[5], strides[4];

@@ -1,5 +1,6 @@
 // Tile plan of the TMA-staged convolution kernel (conv_tma.cu), shared between the host planner and the kernel.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -56,5 +57,19 @@ struct TmaArgs {
 };
 
 int conv_tma_try(const coclr_conv_t& P, int num_sms, cudaStream_t stream);
+
+// host-side description of a tiled tensor map (up to 5 dims; dim 0 = channels, unit stride) over one or two planes
+struct MapSpec {
+  void* base[2];
+  uint64_t dims[5];
+  uint64_t strides[4];   // bytes, dims 1..4
+  uint32_t box[5];
+  int elem_bytes;
+};
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda); plane `which`; false when unavailable
+bool encode_map(CUtensorMap* m, const MapSpec& s, int which, int rank = 5, bool swizzle = true);
+
+// TMA-staged weight gradient (wgrad_tma.cu): 0 = launched, < 0 = error, 1 = shape not covered (caller falls back)
+int wgrad_tma_try(const coclr_wgrad_t& P, cudaStream_t stream);
 
 }  // namespace coclr

@@ -595,6 +595,7 @@ class Plan:
             return
         # ---- backward ----
         bw = self.bwd
+        self.wgrads = []       # every coclr_wgrad_t of the plan (they share one workspace, see the end of this method)
         if g.head_dim is not None:
             self.dq = torch.empty(B, hd, **f32)
             self.dh2 = torch.empty(B, 1, 1, 1, hd, **f32)
@@ -614,6 +615,7 @@ class Plan:
             wg1 = L.Wgrad(sw_feat, one.c(0), s_dh1, B, 1, 1, 1, fs, fs, L.dptr(st.view("2.weight", grad=True)), bnp, 1, 1, 1)
             dg1 = ops.make_conv(s_dh1, 1, one.c(1), B, (1, 1, 1), eng.packed_bwd["2"], self.dfeat, npass=bnp)
             self.keep += [s_dh2, wg2, dg2, s_dh1, wg1, dg1]
+            self.wgrads += [wg2, wg1]
             bw.append((lib.coclr_conv_wgrad, (C.byref(wg2),)))
             bw.append((lib.coclr_conv_igemm, (C.byref(dg2), nsm)))
             bw.append((lib.coclr_bias_relu_bwd, (L.dptr(self.h1), L.dptr(b2), L.dptr(self.dh1),
@@ -706,12 +708,14 @@ class Plan:
                         wg = L.Wgrad(wsrc, geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin_eff,
                                      L.dptr(dw_eff), bnp, gbf, gbf, splits, L.dptr(oscale))
                         self.keep += [wg, dy]
+                        self.wgrads.append(wg)
                         bw.append((eng._s2d_wgrad_op(it.name, wg), ()))
                     else:
                         wg = L.Wgrad(wsrc, geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin,
                                      L.dptr(st.view_span([n + ".weight" for n in it.weight_names], grad=True)), bnp, gbf, gbf,
                                      splits, L.dptr(oscale))
                         self.keep += [wg, dy]
+                        self.wgrads.append(wg)
                         bw.append((lib.coclr_conv_wgrad, (C.byref(wg),)))
                     if it.need_dgrad:
                         dg = ops.make_conv(dy, gbf, geom.c(1), B, sa.dims, eng.packed_bwd[it.name], sa.grad, it.src_coff,
@@ -729,6 +733,14 @@ class Plan:
                 bw.append((lib.coclr_maxpool_bwd, (C.byref(pl),)))
         if any(t.gates for t in g.tensors):
             self.bwd_split = None   # gating parameters sit behind the BatchNorm region: one all-reduce at the end
+        # one workspace for the weight-gradient launches (they run one after the other on the side stream): per-CTA
+        # partial sums are written with plain stores and reduced by a second launch instead of fp32 atomics into dW
+        need = max([int(lib.coclr_wgrad_ws_floats(C.byref(w))) for w in self.wgrads] + [0])
+        self.wg_ws = None
+        if need > 0 and EncoderEngine.wgrad_workspace:
+            self.wg_ws = torch.empty(need, dtype=torch.float32, device=dev)
+            for w in self.wgrads:
+                w.ws, w.ws_floats = L.dptr(self.wg_ws).value, need
 
 
 class EncoderEngine:
@@ -879,7 +891,7 @@ class EncoderEngine:
                 raise L.CoclrError("%s failed with code %d" % (fn.__name__, rc))
         for ln in active:
             main.wait_stream(self._lane_streams[ln])
-        L.LAUNCHES += sum(L.KERNELS_PER_CALL.get(fn.__name__, 1) for fn, _ in oplist)
+        L.LAUNCHES += sum(L.kernels_of(fn, args) for fn, args in oplist)
 
     def _run(self, oplist, side_fn=None):
         """Launch the list on the current stream. Ops whose function is `side_fn` (the weight-gradient GEMMs, which
@@ -912,7 +924,7 @@ class EncoderEngine:
                 raise L.CoclrError("%s failed with code %d" % (fn.__name__, rc))
         if use_side and side_used:
             main.wait_stream(side)
-        L.LAUNCHES += sum(L.KERNELS_PER_CALL.get(fn.__name__, 1) for fn, _ in oplist)
+        L.LAUNCHES += sum(L.kernels_of(fn, args) for fn, args in oplist)
 
     def forward(self, x, training=True, with_backward=False, repack=True, batch_index=None, batch=None, peers=None,
                 norm=None):
@@ -965,6 +977,7 @@ class EncoderEngine:
         return p
 
     use_graphs = os.environ.get("COCLR_GRAPHS", "1") != "0"
+    wgrad_workspace = os.environ.get("COCLR_WGRAD_WS", "1") != "0"
 
     def _graphed(self, p, key, body):
         """Every launch of `body` has fixed pointers and shapes: after one eager run (which also performs the

@@ -44,7 +44,7 @@ class Wgrad(C.Structure):
                 ("B", C.c_int), ("Td", C.c_int), ("Hd", C.c_int), ("Wd", C.c_int),
                 ("Cout", C.c_int), ("Cin_real", C.c_int), ("dw", C.c_void_p),
                 ("npass", C.c_int), ("dy_bf16", C.c_int), ("src_bf16", C.c_int), ("splits", C.c_int),
-                ("out_scale", C.c_void_p)]
+                ("out_scale", C.c_void_p), ("ws", C.c_void_p), ("ws_floats", C.c_long)]
 
 
 class Pack(C.Structure):
@@ -118,7 +118,18 @@ def load():
 
 
 LAUNCHES = 0  # kernels of this library launched so far in this process (bench.py reports the per-step count)
-KERNELS_PER_CALL = {"coclr_bn_bwd": 2, "coclr_l2norm_bwd": 2, "coclr_conv_packed_bytes": 0, "coclr_gate_fc_bwd": 2}
+KERNELS_PER_CALL = {"coclr_bn_bwd": 2, "coclr_l2norm_bwd": 2, "coclr_conv_packed_bytes": 0, "coclr_gate_fc_bwd": 2, "coclr_wgrad_ws_floats": 0, "coclr_wgrad_tma_plan": 0}
+
+
+def kernels_of(fn, args):
+    """Kernels one call of `fn` launches (bench.py reports the per-step total).  A weight gradient on the TMA-staged
+    kernel with a workspace is two launches: partial sums, then the reduction over the pixel splits."""
+    name = fn.__name__
+    if name == "coclr_conv_wgrad" and args and hasattr(args[0], "_obj"):
+        wg = args[0]._obj
+        if wg.ws and load().coclr_wgrad_tma_plan(args[0], None) == 1:
+            return 2
+    return KERNELS_PER_CALL.get(name, 1)
 
 
 def check(rc, what):

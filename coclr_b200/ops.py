@@ -105,8 +105,16 @@ def conv_igemm(src, a_bf16, geom_c, B, dst_dims, pw, dst, dst_coff=0, accumulate
 
 
 def conv_wgrad(src, src_bf16, geom_c, dy_src, dy_bf16, B, dst_dims, Cout, Cin_real, dw, npass=3, splits=1,
-               out_scale=None):
+               out_scale=None, workspace=None):
+    """workspace: optional fp32 tensor (see coclr_wgrad_ws_floats) -- partial sums by plain stores + one reduction
+    launch instead of fp32 atomics; True allocates one of the size the shape asks for."""
     Td, Hd, Wd = dst_dims
     p = L.Wgrad(src, geom_c, dy_src, B, Td, Hd, Wd, Cout, Cin_real, L.dptr(dw), npass, int(dy_bf16), int(src_bf16),
                 splits, L.dptr(out_scale))
+    if workspace is True:
+        need = int(L.load().coclr_wgrad_ws_floats(C.byref(p)))
+        workspace = torch.empty(max(need, 4), dtype=torch.float32, device=dw.device)
+    if workspace is not None:
+        p.ws, p.ws_floats = L.dptr(workspace).value, workspace.numel()
     L.check(L.load().coclr_conv_wgrad(C.byref(p), L.stream_ptr()), "coclr_conv_wgrad")
+    return workspace

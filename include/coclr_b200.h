@@ -99,8 +99,22 @@ typedef struct {
   int dy_bf16, src_bf16;
   int splits;        /* pixel-range splits (>= 1) */
   const float* out_scale; /* device scalar multiplied into the result before it is added to dw, or NULL */
+  float* ws;         /* optional workspace (16-byte aligned) of ws_floats floats, see coclr_wgrad_ws_floats; NULL: none */
+  long ws_floats;
 } coclr_wgrad_t;
 int coclr_conv_wgrad(const coclr_wgrad_t* p, coclr_stream_t stream);
+/* coclr_conv_wgrad runs stride-1 "same" (1,k,k) / (k,1,1) / 1x1x1 shapes on the TMA-staged kernel (csrc/wgrad_tma.cu:
+ * dY tiles and X halo slabs by cp.async.bulk.tensor, the taps of the reuse dimension as the N blocks of one MMA) and
+ * everything else (strided convs, the space-to-depth stem) on the cp.async gather kernel.  Tests / tuning can force the
+ * gather kernel with coclr_set_wgrad_tma(0) or COCLR_WGRAD_TMA=0; `splits` only steers the gather kernel. */
+void coclr_set_wgrad_tma(int enabled);
+/* 1 when the shape runs on the TMA-staged kernel; info[8] (may be NULL) = {tile extent dims 0..2, columns per MMA,
+ * 64-cout blocks per work item, pipeline stages, pixel splits, work items} */
+int coclr_wgrad_tma_plan(const coclr_wgrad_t* p, int* info);
+/* floats of workspace with which the TMA-staged kernel writes its per-CTA partial sums with plain stores and adds them
+ * to dw in one reduction launch (no fp32 atomics: deterministic, and ~2x faster on the many small layers); 0 for shapes
+ * on the gather kernel.  The workspace may be shared by launches on the same stream. */
+long coclr_wgrad_ws_floats(const coclr_wgrad_t* p);
 
 /* ---- weight packing -------------------------------------------------------------------------
  * PyTorch conv weight [Cout, Cin, kt, kh, kw] -> swizzled 16-bit hi/lo tile images.
