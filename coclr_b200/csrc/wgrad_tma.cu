@@ -56,7 +56,8 @@ struct WgPlan {
   WgType type[4];
   int slab_bytes;    // one X load (a multiple of 1024)
   int lbo_bytes;     // distance between consecutive N blocks
-  int N;             // columns of one MMA = 64 * blocks
+  int N;             // columns of one MMA = 64 * blocks (the widest slab type; a type with fewer taps uses 64 * nblk)
+  int win_c, win_kw; // window mode (space-to-depth stem): a 64-element block is win_kw pixels of win_c channels
   int mb;            // 64-cout blocks per item (stacked: 2 = hi / lo plane of the one block)
   int m_groups;      // cout groups
   int m_tiles;       // M = 128 accumulators per item (1 or 2)
@@ -84,7 +85,12 @@ struct WgCol {
 COCLR_DEVINL WgCol wg_col(const WgPlan& L, const WgType& T, int cg, int col) {
   const int blk = col >> 6;
   WgCol r;
-  if (L.nload > 1 || T.nblk == 1) {   // block mode: a block is a channel chunk of the single tap
+  if (L.win_c) {                      // window mode: a block is a kernel row, its 64 elements are (dx, channel)
+    const int within = col & 63;
+    const int dx = within / L.win_c;
+    r.tap = T.tap[blk] * L.win_kw + dx;
+    r.c = within - dx * L.win_c;
+  } else if (L.nload > 1 || T.nblk == 1) {   // block mode: a block is a channel chunk of the single tap
     r.tap = T.tap[0];
     r.c = (cg * L.nload + blk) * 64 + (col & 63);
   } else {                            // slab mode: a block is a tap of the reuse dimension
@@ -140,6 +146,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
   const WgType& T = L.type[type_i];
+  const int Nt = L.nload > 1 ? L.N : 64 * T.nblk;     // columns of this item's MMAs
   const uint32_t dy_plane_bytes = (uint32_t)L.mb * kWgBlockBytes;
   const uint32_t x_plane_bytes = (uint32_t)L.nload * (uint32_t)L.slab_bytes;
 
@@ -193,7 +200,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_con
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc(P.dy_bf16 ? 1u : 0u, P.src_bf16 ? 1u : 0u, 1u, 1u, 128u, (uint32_t)L.N);
+    const uint32_t idesc = make_idesc(P.dy_bf16 ? 1u : 0u, P.src_bf16 ? 1u : 0u, 1u, 1u, 128u, (uint32_t)Nt);
     uint32_t stage = 0, phase = 0;
     for (int it = 0; it < ntile; ++it) {
       mbar_wait_spin(&full_bar[stage], phase);
@@ -250,7 +257,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_con
         n = (mg * L.mb + mt * 2) * 64 + row;
         if (mt * 2 + (row >> 6) >= L.mb) n = L.Cout;  // the upper half of an odd last M tile read a foreign block
       }
-      for (int c0 = 0; c0 < L.N; c0 += 32) {
+      for (int c0 = 0; c0 < Nt; c0 += 32) {
         uint32_t v[32];
         if (ntile > 0) {
           tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * L.N + c0), v);
@@ -264,11 +271,20 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; ++j) dst[(size_t)j * R] = __uint_as_float(v[j]);
         } else if (n < L.Cout && ntile > 0) {
-          const WgCol k = wg_col(L, T, cg, c0);
-          float* dst = P.dw + ((size_t)n * L.Cin_real + k.c) * L.taps + k.tap;
+          if (L.win_c) {                               // window mode: (tap, channel) changes every win_c columns
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (k.c + j < L.Cin_real) atomicAdd(dst + (size_t)j * L.taps, __uint_as_float(v[j]) * os);
+            for (int j = 0; j < 32; ++j) {
+              const WgCol k = wg_col(L, T, cg, c0 + j);
+              if (k.c < L.Cin_real)
+                atomicAdd(P.dw + ((size_t)n * L.Cin_real + k.c) * L.taps + k.tap, __uint_as_float(v[j]) * os);
+            }
+          } else {
+            const WgCol k = wg_col(L, T, cg, c0);
+            float* dst = P.dw + ((size_t)n * L.Cin_real + k.c) * L.taps + k.tap;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (k.c + j < L.Cin_real) atomicAdd(dst + (size_t)j * L.taps, __uint_as_float(v[j]) * os);
+          }
         }
       }
     }
@@ -295,7 +311,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgArgs P) {
   const int rows = L.stacked ? 64 : L.mb * 64;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int col = idx / rows, r = idx - col * rows;
-  if (col >= L.N) return;
+  if (col >= (L.nload > 1 ? L.N : 64 * L.type[type_i].nblk)) return;
   const int n = L.stacked ? r : mg * L.mb * 64 + r;
   const WgCol k = wg_col(L, L.type[type_i], cg, col);
   if (n >= L.Cout || k.c >= L.Cin_real) return;
@@ -338,9 +354,15 @@ static bool wgrad_tma_plan(const coclr_wgrad_t& P, bool with_ws, WgPlan& L, MapS
   const coclr_src_t& D = P.dy;
   memset(&L, 0, sizeof(L));
   if (P.npass != 1 && P.npass != 3) return false;
-  if (g.transposed || g.st != 1 || g.sh != 1 || g.sw != 1) return false;
-  if (S.T != P.Td || S.H != P.Hd || S.W != P.Wd) return false;          // "same" convolutions only
+  if (g.transposed || g.sh != 1 || g.sw != 1 || (g.st != 1 && g.st != 2)) return false;
   if (D.T != P.Td || D.H != P.Hd || D.W != P.Wd) return false;
+  // window kind (the space-to-depth stem, see conv_tma.cu): the kw taps of a kernel row are kw consecutive pixels of
+  // 64 / kw channels = one 128-byte run, read through a tensor map whose pixel stride is smaller than its inner extent
+  const bool window = g.kt == 1 && g.kw > 1 && S.C * g.kw == 64 && S.ld == S.C && S.coff == 0 && g.pw == 0 &&
+                      g.st == 1 && S.W >= P.Wd + g.kw - 1 && S.H == P.Hd && S.T == P.Td;
+  const bool tstride = g.st == 2 && g.kh == 1 && g.kw == 1 && g.kt > 1;
+  if (g.st == 2 && !tstride) return false;
+  if (!window && !tstride && (S.T != P.Td || S.H != P.Hd || S.W != P.Wd)) return false;   // else "same" convs only
   if (S.C % 8 || D.C % 8 || S.ld % 8 || D.ld % 8 || S.coff % 8 || D.coff % 8) return false;
   if (P.npass > 1 && (!S.lo || !D.lo)) return false;
   if (((uintptr_t)S.hi | (uintptr_t)D.hi | (uintptr_t)S.lo | (uintptr_t)D.lo) & 15) return false;
@@ -379,6 +401,40 @@ static bool wgrad_tma_plan(const coclr_wgrad_t& P, bool with_ws, WgPlan& L, MapS
     L.slab_bytes = kWgBlockBytes;
     L.lbo_bytes = kWgBlockBytes;
     L.N = 64 * L.nload;
+  } else if (window) {
+    // ---- space-to-depth stem: (1, kh, kw) over 64/kw-channel pixels; ONE slab serves all kh * kw taps: its blocks are
+    // the kernel rows, the 64 elements of a block the kw pixels x channels of that row ----
+    static const int kNw[2] = {8, 16}, kNh[2] = {8, 4};
+    int best = -1;
+    long best_px = 0;
+    for (int v = 0; v < 2; ++v) {
+      const long px = (long)wg_ceil_div(P.Wd, kNw[v]) * kNw[v] * wg_ceil_div(P.Hd, kNh[v]) * kNh[v];
+      if (best < 0 || px < best_px) { best = v; best_px = px; }
+    }
+    const int nw = kNw[best], nh = kNh[best];
+    if (2 * (long)P.Wd * P.Hd < best_px || g.kh > 4) return false;
+    L.box[0] = nw; L.box[1] = nh;
+    L.ntiles[0] = wg_ceil_div(P.Wd, nw); L.ntiles[1] = wg_ceil_div(P.Hd, nh); L.ntiles[2] = P.Td; L.ntiles[3] = P.B;
+    DY.dims[0] = D.C; DY.dims[1] = P.Wd; DY.dims[2] = P.Hd; DY.dims[3] = P.Td; DY.dims[4] = P.B;
+    DY.strides[0] = ldd; DY.strides[1] = ldd * P.Wd; DY.strides[2] = ldd * P.Wd * P.Hd;
+    DY.strides[3] = ldd * P.Wd * P.Hd * P.Td;
+    DY.box[0] = 64; DY.box[1] = nw; DY.box[2] = nh; DY.box[3] = DY.box[4] = 1;
+    X.dims[0] = 64; X.dims[1] = P.Wd; X.dims[2] = S.H; X.dims[3] = S.T; X.dims[4] = P.B;
+    X.strides[0] = ldx; X.strides[1] = ldx * S.W; X.strides[2] = ldx * S.W * S.H; X.strides[3] = ldx * S.W * S.H * S.T;
+    X.box[0] = 64; X.box[1] = nw; X.box[2] = nh + g.kh - 1; X.box[3] = X.box[4] = 1;
+    reuse = g.kh;
+    L.n_types = 1;
+    L.type[0].d[1] = -g.ph;
+    L.type[0].nblk = g.kh;
+    for (int j = 0; j < g.kh; ++j) L.type[0].tap[j] = j;
+    L.nc = 1;
+    L.nload = 1;
+    L.n_cgroups = 1;
+    L.win_c = S.C;
+    L.win_kw = g.kw;
+    L.slab_bytes = nw * (nh + g.kh - 1) * 128;
+    L.lbo_bytes = nw * 128;
+    L.N = 64 * g.kh;
   } else if (g.kt == 1) {
     // ---- (1, kh, kw): tiles of nw x nh pixels, one slab type per dx, the kh taps of a column share the slab ----
     static const int kNw[3] = {16, 8, 32}, kNh[3] = {4, 8, 2};
@@ -428,24 +484,47 @@ static bool wgrad_tma_plan(const coclr_wgrad_t& P, bool with_ws, WgPlan& L, MapS
     if (2 * (long)HW * P.Td < best_px) return false;
     L.box[0] = npx; L.box[2] = nt;
     L.ntiles[0] = wg_ceil_div(HW, npx); L.ntiles[2] = wg_ceil_div(P.Td, nt); L.ntiles[3] = P.B;
-    for (MapSpec* m : {&DY, &X}) {
-      const long ld = m == &DY ? ldd : ldx;
-      m->dims[0] = m == &DY ? D.C : S.C; m->dims[1] = HW; m->dims[2] = 1; m->dims[3] = P.Td; m->dims[4] = P.B;
-      m->strides[0] = ld; m->strides[1] = ld * HW; m->strides[2] = ld * HW; m->strides[3] = ld * HW * P.Td;
-      m->box[0] = 64; m->box[1] = npx; m->box[2] = 1; m->box[3] = nt; m->box[4] = 1;
-    }
-    X.box[3] = nt + g.kt - 1;
-    reuse = g.kt;
-    L.n_types = 1;
-    WgType& t = L.type[0];
-    t.d[2] = -g.pt;
-    t.nblk = g.kt;
-    for (int j = 0; j < g.kt; ++j) t.tap[j] = j;
+    DY.dims[0] = D.C; DY.dims[1] = HW; DY.dims[2] = 1; DY.dims[3] = P.Td; DY.dims[4] = P.B;
+    DY.strides[0] = ldd; DY.strides[1] = ldd * HW; DY.strides[2] = ldd * HW; DY.strides[3] = ldd * HW * P.Td;
+    DY.box[0] = 64; DY.box[1] = npx; DY.box[2] = 1; DY.box[3] = nt; DY.box[4] = 1;
     L.nload = 1;
     L.n_cgroups = L.nc;
-    L.slab_bytes = npx * (nt + g.kt - 1) * 128;
     L.lbo_bytes = npx * 128;
-    L.N = 64 * g.kt;
+    if (!tstride) {
+      X.dims[0] = S.C; X.dims[1] = HW; X.dims[2] = 1; X.dims[3] = S.T; X.dims[4] = P.B;
+      X.strides[0] = ldx; X.strides[1] = ldx * HW; X.strides[2] = ldx * HW; X.strides[3] = ldx * HW * S.T;
+      X.box[0] = 64; X.box[1] = npx; X.box[2] = 1; X.box[3] = nt + g.kt - 1; X.box[4] = 1;
+      reuse = g.kt;
+      L.n_types = 1;
+      WgType& t = L.type[0];
+      t.d[2] = -g.pt;
+      t.nblk = g.kt;
+      for (int j = 0; j < g.kt; ++j) t.tap[j] = j;
+    } else {
+      // temporal stride 2 (the stem's (7,1,1) conv): input frame 2 * t' - pt + dt = 2 * (t' + sh) + par; the X map
+      // splits the frames by parity, [C, HW, 2, T / 2, B], and there is one slab type per parity
+      if (S.H != P.Hd || S.W != P.Wd || S.T % 2 != 0 || (S.T + 2 * g.pt - g.kt) / 2 + 1 != P.Td) return false;
+      X.dims[0] = S.C; X.dims[1] = HW; X.dims[2] = 2; X.dims[3] = S.T / 2; X.dims[4] = P.B;
+      X.strides[0] = ldx; X.strides[1] = ldx * HW; X.strides[2] = ldx * HW * 2; X.strides[3] = ldx * HW * S.T;
+      L.n_types = 2;
+      for (int par = 0; par < 2; ++par) {
+        WgType& t = L.type[par];
+        t.nblk = 0;
+        for (int dt = 0; dt < g.kt; ++dt) {
+          const int rel = dt - g.pt;
+          if ((((rel % 2) + 2) % 2) != par) continue;
+          const int sh = (rel - par) / 2;            // exact
+          if (t.nblk == 0) t.d[2] = sh;               // taps of one parity are consecutive shifts
+          t.tap[t.nblk++] = dt;
+        }
+        t.d[1] = par;
+        if (t.nblk == 0) return false;
+        if (t.nblk > reuse) reuse = t.nblk;
+      }
+      X.box[0] = 64; X.box[1] = npx; X.box[2] = 1; X.box[3] = nt + reuse - 1; X.box[4] = 1;
+    }
+    L.slab_bytes = npx * (nt + reuse - 1) * 128;
+    L.N = 64 * reuse;
   } else {
     return false;
   }

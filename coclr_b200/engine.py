@@ -595,7 +595,7 @@ class Plan:
             return
         # ---- backward ----
         bw = self.bwd
-        self.wgrads = []       # every coclr_wgrad_t of the plan (they share one workspace, see the end of this method)
+        self.wgrads, self.s2d_wgrads = [], []   # coclr_wgrad_t structs of the plan (workspaces: end of this method)
         if g.head_dim is not None:
             self.dq = torch.empty(B, hd, **f32)
             self.dh2 = torch.empty(B, 1, 1, 1, hd, **f32)
@@ -708,7 +708,7 @@ class Plan:
                         wg = L.Wgrad(wsrc, geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin_eff,
                                      L.dptr(dw_eff), bnp, gbf, gbf, splits, L.dptr(oscale))
                         self.keep += [wg, dy]
-                        self.wgrads.append(wg)
+                        self.s2d_wgrads.append(wg)
                         bw.append((eng._s2d_wgrad_op(it.name, wg), ()))
                     else:
                         wg = L.Wgrad(wsrc, geom.c(0), dy, B, a.dims[0], a.dims[1], a.dims[2], it.cout, it.cin,
@@ -741,6 +741,14 @@ class Plan:
             self.wg_ws = torch.empty(need, dtype=torch.float32, device=dev)
             for w in self.wgrads:
                 w.ws, w.ws_floats = L.dptr(self.wg_ws).value, need
+            # the space-to-depth stem's weight gradient runs on the main stream (it is followed by a scatter into the
+            # real weight layout) while the others may still be busy on the side stream: its own workspace
+            for w in self.s2d_wgrads:
+                n_own = int(lib.coclr_wgrad_ws_floats(C.byref(w)))
+                if n_own > 0:
+                    own = torch.empty(n_own, dtype=torch.float32, device=dev)
+                    self.keep.append(own)
+                    w.ws, w.ws_floats = L.dptr(own).value, n_own
 
 
 class EncoderEngine:

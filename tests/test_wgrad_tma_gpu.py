@@ -134,3 +134,86 @@ def test_benchmark_shapes_take_the_tma_kernel():
             missed.append((cin, cout, k, T, H, W))
     # (1,3,3) convs on 4x4 frames would pad more than half of every 8x8 tile: those stay on the gather kernel
     assert all(k == (1, 3, 3) and H == 4 for _, _, k, _, H, _ in missed), missed
+
+
+def _run_modes(lib, L, make_wg, dw_shape, diag, key):
+    """workspace epilogue / atomic epilogue / gather kernel on the same struct; returns the three results"""
+    res = {}
+    for mode in (2, 1, 0):
+        lib.coclr_set_wgrad_tma(int(mode > 0))
+        dw = torch.zeros(dw_shape, device="cuda")
+        wg = make_wg(dw)
+        if mode == 2:
+            need = int(lib.coclr_wgrad_ws_floats(C.byref(wg)))
+            assert need > 0, "shape not on the TMA-staged kernel"
+            ws = torch.full((need,), float("nan"), device="cuda")
+            wg.ws, wg.ws_floats = L.dptr(ws).value, need
+        if mode > 0:
+            info = (C.c_int * 8)()
+            assert lib.coclr_wgrad_tma_plan(C.byref(wg), info) == 1
+            diag[key + "/plan%d" % mode] = list(info)
+        L.check(lib.coclr_conv_wgrad(C.byref(wg), L.stream_ptr()), "coclr_conv_wgrad")
+        torch.cuda.synchronize()
+        res[mode] = dw
+    lib.coclr_set_wgrad_tma(1)
+    return res
+
+
+@pytest.mark.parametrize("dims", [(1, 8, 16, 16), (2, 6, 10, 12)], ids=["even", "ragged"])
+def test_wgrad_tma_temporal_stride2(dims, diag):
+    """The stem's (7,1,1) conv with temporal stride 2 (backbone/s3dg.py:145 Conv_1a.conv2): frames split by parity in
+    the tensor map, one halo slab per parity (taps dt = 0,2,4,6 and 1,3,5)."""
+    from coclr_b200 import ops, lib as L
+    lib = L.load()
+    B, T, H, W = dims
+    Cin = Cout = 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.relu(torch.randn(B, Cin, T, H, W, device="cuda", generator=g))
+    geom = ops.Geometry((7, 1, 1), (2, 1, 1), (3, 0, 0))
+    To, Ho, Wo = geom.out_dims(T, H, W)
+    dy = torch.randn(B, Cout, To, Ho, Wo, device="cuda", generator=g)
+    xp, Cp = _planes(ops, x, 0, True, 8, 16)
+    dp, Cop = _planes(ops, dy, 0, True, 16, 8)
+    xv = xp.value()[..., 8:8 + Cin].permute(0, 4, 1, 2, 3).double()
+    dv = dp.value()[..., 16:16 + Cout].permute(0, 4, 1, 2, 3).double()
+    wd = torch.zeros(Cout, Cin, 7, 1, 1, device="cuda", dtype=torch.float64, requires_grad=True)
+    (ref,) = torch.autograd.grad(F.conv3d(xv, wd, stride=(2, 1, 1), padding=(3, 0, 0)), wd, dv)
+    mk = lambda dw: L.Wgrad(xp.src(8, Cp, T, H, W), geom.c(0), dp.src(16, Cop, To, Ho, Wo), B, To, Ho, Wo, Cout, Cin,
+                            L.dptr(dw), 3, 0, 0, 3, None)
+    res = _run_modes(lib, L, mk, (Cout, Cin, 7, 1, 1), diag, "wgrad_tma/stem_tm_%d" % T)
+    errs = [_rel(res[m], ref) for m in (2, 1, 0)]
+    diag["wgrad_tma/stem_tm_%d" % T] = errs
+    assert max(errs) < 2e-5, errs
+
+
+@pytest.mark.parametrize("dims", [(1, 2, 16, 16), (2, 3, 12, 24)], ids=["even", "ragged"])
+def test_wgrad_tma_space_to_depth_window(dims, diag):
+    """The space-to-depth stem as the engine launches it (backbone/s3dg.py:145 Conv_1a.conv1 as a stride-1 (1,4,4) conv
+    over 16-channel pixels, rows zero-padded by 2 pixels on each side, pw = 0): one slab serves all 16 taps."""
+    from coclr_b200 import ops, lib as L
+    lib = L.load()
+    B, T, H, W = dims
+    Cout, Cin = 64, 12
+    g = torch.Generator(device="cuda").manual_seed(6)
+    xpl = ops.Planes((B, T, H, W + 4, 16), 0, "cuda", zero=True)
+    vals = torch.randn(B, T, H, W, 12, device="cuda", generator=g)
+    tmp = ops.Planes((B, T, H, W, 16), 0, "cuda", zero=True)
+    rows = torch.zeros(B * T * H * W, 16, device="cuda")
+    rows[:, :12] = vals.view(-1, 12)
+    ops.split_into(rows, tmp)
+    xpl.hi[:, :, :, 2:-2] = tmp.hi
+    xpl.lo[:, :, :, 2:-2] = tmp.lo
+    dy = torch.randn(B, Cout, T, H, W, device="cuda", generator=g)
+    dp, Cop = _planes(ops, dy, 0, True, 0, 0)
+    geom = ops.Geometry((1, 4, 4), (1, 1, 1), (0, 2, 0))
+    xv = xpl.value()[..., :12].permute(0, 4, 1, 2, 3).double()              # [B, 12, T, H, W + 4]
+    dv = dp.value()[..., :Cout].permute(0, 4, 1, 2, 3).double()
+    wd = torch.zeros(Cout, Cin, 1, 4, 4, device="cuda", dtype=torch.float64, requires_grad=True)
+    y = F.conv3d(xv, wd, padding=(0, 2, 0))[:, :, :, :H, :W]                # the H x W destination pixels the engine uses
+    (ref,) = torch.autograd.grad(y, wd, dv)
+    mk = lambda dw: L.Wgrad(xpl.src(0, 16, T, H, W + 4), geom.c(0), dp.src(0, Cop, T, H, W), B, T, H, W, Cout, Cin,
+                            L.dptr(dw), 3, 0, 0, 3, None)
+    res = _run_modes(lib, L, mk, (Cout, Cin, 1, 4, 4), diag, "wgrad_tma/s2d_%d" % W)
+    errs = [_rel(res[m], ref) for m in (2, 1, 0)]
+    diag["wgrad_tma/s2d_%d" % W] = errs
+    assert max(errs) < 2e-5, errs
