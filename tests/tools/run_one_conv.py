@@ -45,15 +45,15 @@ elif mode == "dgrad":
 else:
     x = ops.Planes((B, T, H, W, r8(Cin)), 1, dev)
     x.hi.normal_(); x.lo.normal_(0, 1e-3)
-    dy = ops.Planes((B, T, H, W, r8(Cout)), 1, dev)
+    dy = ops.Planes((B, To, Ho, Wo, r8(Cout)), 1, dev)
     dy.hi.normal_(); dy.lo.normal_(0, 1e-3)
     dw = torch.zeros_like(w)
     splits = int(os.environ.get("SPLITS", "50"))
     ws = [True if os.environ.get("WS") else None]     # WS=1: workspace epilogue of the TMA-staged kernel
 
     def run():
-        ws[0] = ops.conv_wgrad(x.src(0, r8(Cin), T, H, W), 1, geom.c(0), dy.src(0, r8(Cout), T, H, W), 1, B, (T, H, W),
-                               Cout, Cin, dw, npass=npass, splits=splits, workspace=ws[0])
+        ws[0] = ops.conv_wgrad(x.src(0, r8(Cin), T, H, W), 1, geom.c(0), dy.src(0, r8(Cout), To, Ho, Wo), 1, B,
+                               (To, Ho, Wo), Cout, Cin, dw, npass=npass, splits=splits, workspace=ws[0])
 for _ in range(2):
     run()
 torch.cuda.synchronize()
