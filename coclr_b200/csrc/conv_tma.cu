@@ -346,9 +346,16 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
     named_bar_sync(1, 128);
     const uint32_t my_stage = stage_base + (uint32_t)warp * (uint32_t)L.stage_bufs * kStageBytes;
-    float s1[8], s2[8];
+    // BatchNorm statistics: per column, sum and sum of squares of d = x - x0 in fp32, where x0 is the first value of
+    // the column this CTA sees; converted exactly in double when they leave the CTA:
+    //   sum x = sum d + n x0,  sum x^2 = sum d^2 + 2 x0 sum d + n x0^2,
+    // so that var = E[x^2] - mean^2 (formed in double by the finalize step) does not lose the variance of channels whose
+    // spread is small against their mean to fp32 rounding of the raw sums (nn.BatchNorm3d is two-pass)
+    float s1[8], s2[8], x0[8];
+    uint32_t x0_set = 0u;
+    int nrows = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = x0[i] = 0.f;
     // box-relative position of this lane's row (rows are in box order, dim 1 fastest)
     int ri[4];
     {
@@ -422,21 +429,30 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           if (want_stats && !(L.dbg & 2)) {
             // lane c sums column c over the warp's valid rows, reading the swizzled block back (conflict-free; a variant
             // with 16-byte reads + shuffle reduction measured slower)
-            float a = 0.f, b = 0.f;
-            const uint32_t cchunk = (uint32_t)lane >> 2, cword = ((uint32_t)lane & 3u) << 2;
-#pragma unroll 8
-            for (uint32_t r = 0; r < 32; ++r) {
-              if ((vmask >> r) & 1u) {
-                const float x = ld_shared_f32(buf + r * 128u + ((cchunk ^ (r & 7u)) << 4) + cword);
-                a += x;
-                b = fmaf(x, x, b);
+            if (vmask != 0u) {
+              float a = 0.f, b = 0.f;
+              const uint32_t cchunk = (uint32_t)lane >> 2, cword = ((uint32_t)lane & 3u) << 2;
+              if (!((x0_set >> kq) & 1u)) {
+                const uint32_t r0 = (uint32_t)__ffs((int)vmask) - 1u;
+                x0[kq] = ld_shared_f32(buf + r0 * 128u + ((cchunk ^ (r0 & 7u)) << 4) + cword);
+                x0_set |= 1u << kq;
               }
+              const float xs = x0[kq];
+#pragma unroll 8
+              for (uint32_t r = 0; r < 32; ++r) {
+                if ((vmask >> r) & 1u) {
+                  const float d = ld_shared_f32(buf + r * 128u + ((cchunk ^ (r & 7u)) << 4) + cword) - xs;
+                  a += d;
+                  b = fmaf(d, d, b);
+                }
+              }
+              s1[kq] += a;
+              s2[kq] += b;
             }
-            s1[kq] += a;
-            s2[kq] += b;
           }
         }
       }
+      nrows += __popc(vmask);
       tc_fence_before();
       __syncwarp();
       if (leader) {
@@ -448,11 +464,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         for (int kq = 0; kq < 8; ++kq) {
           const int col = t.n_tile * L.BN + kq * 32 + lane;
           if (kq * 32 < L.BN && col < L.N) {
-            atomicAdd(&P.stats_sum[col], (double)s1[kq]);
-            atomicAdd(&P.stats_sq[col], (double)s2[kq]);
+            const double n = (double)nrows, xd = (double)x0[kq];
+            atomicAdd(&P.stats_sum[col], (double)s1[kq] + n * xd);
+            atomicAdd(&P.stats_sq[col], (double)s2[kq] + xd * (2.0 * (double)s1[kq] + n * xd));
           }
           s1[kq] = s2[kq] = 0.f;
         }
+        x0_set = 0u;
+        nrows = 0;
       }
     }
     if (leader) bulk_wait_group_read<0>();
@@ -460,20 +479,21 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     if (want_stats && L.n_tiles_n == 1) {
       // combine the four warps' column sums in shared memory (the staging blocks are free now), one fp64 atomic per
       // channel and CTA
-      float* tab = reinterpret_cast<float*>(smem + L.off_stage);   // [4 warps][2][256]
+      double* tab = reinterpret_cast<double*>(smem + L.off_stage);   // [4 warps][2][256] = 16 KB = the staging blocks
       named_bar_sync(1, 128);
 #pragma unroll
       for (int kq = 0; kq < 8; ++kq) {
-        tab[(warp * 2 + 0) * 256 + kq * 32 + lane] = s1[kq];
-        tab[(warp * 2 + 1) * 256 + kq * 32 + lane] = s2[kq];
+        const double n = (double)nrows, xd = (double)x0[kq];
+        tab[(warp * 2 + 0) * 256 + kq * 32 + lane] = (double)s1[kq] + n * xd;
+        tab[(warp * 2 + 1) * 256 + kq * 32 + lane] = (double)s2[kq] + xd * (2.0 * (double)s1[kq] + n * xd);
       }
       named_bar_sync(1, 128);
       for (int c = threadIdx.x; c < L.N; c += 128) {
         double a = 0.0, b = 0.0;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          a += (double)tab[(w * 2 + 0) * 256 + c];
-          b += (double)tab[(w * 2 + 1) * 256 + c];
+          a += tab[(w * 2 + 0) * 256 + c];
+          b += tab[(w * 2 + 1) * 256 + c];
         }
         atomicAdd(&P.stats_sum[c], a);
         atomicAdd(&P.stats_sq[c], b);
