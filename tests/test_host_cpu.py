@@ -434,6 +434,36 @@ def test_reference_adam_state_converts_to_flat(tmp_path):
         L.DRY_RUN = False
 
 
+def test_weight_gradient_workspaces_dry_run():
+    """Workspace wiring of the weight-gradient launches (host logic on the dry-run plan): the launches that go to the
+    side stream share ONE workspace big enough for each of them; the space-to-depth stem's launch, which runs on the main
+    stream while the side stream may still be busy, has its own; nothing overlaps."""
+    import ctypes as C
+    from coclr_b200 import lib as L, engine as E
+    from coclr_b200.s3d_spec import s3d_stages
+    lib = L.load()
+    L.DRY_RUN = True
+    try:
+        g = E.Graph(s3d_stages(3), 3, head_dim=128, bb_prefix="0.")
+        st = E.ParamStore(g, "cpu")
+        eng = E.EncoderEngine(st, g, "parity")
+        p = eng.plan(2, 8, 64, 64, True, True)
+        assert len(p.wgrads) + len(p.s2d_wgrads) == 77 - (9 if g.fuse_b12 else 0) + 2 and len(p.s2d_wgrads) == 1
+        shared = {w.ws for w in p.wgrads}
+        assert len(shared) == 1 and p.wg_ws is not None and shared == {p.wg_ws.data_ptr()}
+        need = [int(lib.coclr_wgrad_ws_floats(C.byref(w))) for w in p.wgrads]
+        assert max(need) == p.wg_ws.numel() and all(w.ws_floats == p.wg_ws.numel() for w in p.wgrads)
+        assert sum(1 for n in need if n > 0) >= 45           # all but the (1,3,3) convs on 4x4 / 2x2 frames at this shape
+        own = p.s2d_wgrads[0]
+        lo, hi = p.wg_ws.data_ptr(), p.wg_ws.data_ptr() + 4 * p.wg_ws.numel()
+        assert own.ws and not (lo <= own.ws < hi) and own.ws_floats == int(lib.coclr_wgrad_ws_floats(C.byref(own))) > 0
+        # launch accounting: a weight gradient with a workspace is two kernels
+        wl = [(fn, a) for fn, a in p.bwd if fn.__name__ == "coclr_conv_wgrad"]
+        assert sum(L.kernels_of(fn, a) for fn, a in wl) == len(wl) + sum(1 for n in need if n > 0)
+    finally:
+        L.DRY_RUN = False
+
+
 def test_overlapped_allreduce_ranges_are_final_when_reduced():
     """The flat gradient is all-reduced in two parts (moco._EncodeFn.backward): the first part while the second segment
     of the backward launch list still runs.  Host logic, checked on the dry-run plan: the two range sets partition the
