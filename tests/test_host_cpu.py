@@ -434,6 +434,37 @@ def test_reference_adam_state_converts_to_flat(tmp_path):
         L.DRY_RUN = False
 
 
+def test_weight_gradient_plans_cover_the_benchmark_shapes():
+    """Host-side planner of the TMA-staged weight-gradient kernel (no launch, no GPU): at B=32, T=32, 128^2 every
+    weight gradient of S3D -- the space-to-depth stem and the temporally strided stem conv included -- is covered,
+    except the (1,3,3) convs on 4x4 frames (tiles would be more than half padding)."""
+    import ctypes as C
+    from coclr_b200 import lib as L, engine as E
+    from coclr_b200.s3d_spec import s3d_stages
+    lib = L.load()
+    L.DRY_RUN = True
+    try:
+        g = E.Graph(s3d_stages(3), 3, head_dim=128, bb_prefix="0.")
+        st = E.ParamStore(g, "cpu")
+        eng = E.EncoderEngine(st, g, "parity")
+        p = eng.plan(2, 32, 128, 128, True, True)     # the planner only looks at T, H, W and the channel counts
+        info = (C.c_int * 8)()
+        missed, kinds = [], {}
+        for w in p.wgrads + p.s2d_wgrads:
+            gm = w.g
+            key = (gm.kt, gm.kh, gm.kw, gm.st)
+            if lib.coclr_wgrad_tma_plan(C.byref(w), info) == 1:
+                kinds[key] = kinds.get(key, 0) + 1
+                assert info[3] in (64, 128, 192, 256) and 1 <= info[4] <= 4 and info[5] >= 2
+            else:
+                missed.append((key, w.Hd, w.Wd))
+        assert all(k == (1, 3, 3, 1) and h == 4 for k, h, _ in missed) and len(missed) == 4, missed
+        assert kinds[(1, 4, 4, 1)] == 1 and kinds[(7, 1, 1, 2)] == 1        # both stem layers
+        assert kinds[(1, 3, 3, 1)] == 15 and kinds[(3, 1, 1, 1)] == 19 and kinds[(1, 1, 1, 1)] == 1 + 3 * 9 + 2
+    finally:
+        L.DRY_RUN = False
+
+
 def test_weight_gradient_workspaces_dry_run():
     """Workspace wiring of the weight-gradient launches (host logic on the dry-run plan): the launches that go to the
     side stream share ONE workspace big enough for each of them; the space-to-depth stem's launch, which runs on the main
