@@ -546,7 +546,10 @@ def main():
                 "launches_per_step": cv["launches"], "ms_per_step_in_kernel": cv["ms"],
                 "mode": "%s (forward %s, backward %s)" % (args.precision,
                                                         "3 MMA passes fp16 hi/lo" if args.precision != "fast" else "1 pass bf16",
-                                                        "3 MMA passes bf16 hi/lo" if args.precision == "parity" else "1 pass bf16"),
+                                                        "3 MMA passes fp16 hi/lo, gradient planes scaled by a per-tensor power of two"
+                                                        if args.precision == "parity" else
+                                                        ("1 pass fp16 on the scaled gradient planes" if args.precision == "mixed"
+                                                         else "1 pass bf16")),
                 "tensor_work_frac": (achieved * 3 / peak_tf) if passes else None,
                 "wgrad": {"achieved": wg["flops"] / (wg["ms"] * 1e-3) / 1e12 if wg["ms"] > 0 else 0.0,
                           "ms_per_step_in_kernel": wg["ms"], "launches_per_step": wg["launches"]},
